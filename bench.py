@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the COVIDCurve hot path on B200 (and of the CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--vectors V] [--mcmc-iters I]
+
+Workload (BASELINE.json configs[4] = "cfg5", the likelihood-only microbenchmark on the configs[2] shape the metric
+is quoted on): V (default 2^20) random parameter vectors per GPU of the 10-age-band / 300-day / 5-knot / 3-serosurvey
+binomial model (d = 34), synthetic data (covidcurve_b200/synth.py, seeds 20201/20202).  One "step" = one pass of
+the batched log-likelihood over all V vectors.  `value` = log-likelihood evaluations per second, whole job
+(all ranks), inputs resident in HBM.  `e2e` = the same through the C ABI with HOST (pinned) buffers: host->device
+copy of the parameter vectors and device->host copy of the log-likelihoods inside the timed region.
+`mcmc` = GPU-resident Metropolis-coupled MCMC on configs[2] (64 chains x 50 rungs per GPU): iterations/s summed over
+all chains x rungs (one iteration = one sweep of d single-site updates + the coupling pass).
+
+Multi-GPU: launched by torchrun, one rank per GPU; vectors / chains are sharded with no data-path collective (weak
+scaling: V vectors and 64 x 50 particles per GPU); timing = max over ranks of CUDA-event time between barriers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from covidcurve_b200 import synth  # noqa: E402
+
+METRIC = "loglike_evals_per_sec"
+UNIT = "evals/s"
+
+
+def f_alg(spec):
+    """Algorithmic flops per full evaluation: T(T+1) + serorev*M(M+1) + 3*S*M + 10*T."""
+    T, M, S = spec.T, spec.M, spec.S
+    return T * (T + 1) + (M * (M + 1) if spec.account_serorev else 0) + 3 * S * M + 10 * T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_rate(spec, theta, seconds, threads):
+    """evals/s of the CPU oracle (loop-for-loop restatement of the reference, g++ -O2) on `threads` host threads."""
+    from oracle.oracle import Oracle
+    o = Oracle(spec)
+    probe = theta[: 64 * threads]
+    t0 = time.perf_counter()
+    o.loglike(probe, nthreads=threads)
+    rate = len(probe) / (time.perf_counter() - t0)
+    n = int(max(threads * 64, min(len(theta), rate * seconds)))
+    t0 = time.perf_counter()
+    o.loglike(theta[:n], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference itself needs
+    R + Rcpp + libRmath, absent from this image) with all host threads, on the same config / metric."""
+    if rank != 0:
+        return
+    spec, _ = synth.make_spec("cfg3")
+    cores = os.cpu_count() or 1
+    per_step = args.ref_vectors
+    theta = synth.random_theta(spec, per_step, seed=synth.SEED_THETA, bad_frac=0.01)
+    from oracle.oracle import Oracle
+    o = Oracle(spec)
+    for _ in range(args.warmup):
+        o.loglike(theta[: max(cores * 16, per_step // 8)], nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.loglike(theta, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "%d random cfg5 vectors per step (seed %d), %d threads, g++ -O2 oracle port" % (per_step, synth.SEED_THETA, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg5: likelihood-only, 10 age bands x 300 days x 5 knots x 3 serosurveys, binomial (d=34)",
+                   "vectors_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--vectors", type=int, default=1 << 20, help="parameter vectors per GPU per step")
+    ap.add_argument("--ref-vectors", type=int, default=8192, help="vectors per step of the CPU reference arm")
+    ap.add_argument("--mcmc-iters", type=int, default=30, help="timed MCMC iterations (0 = skip the MCMC leg)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from covidcurve_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    spec, truth = synth.make_spec("cfg3")
+    d, V = spec.d, args.vectors
+    model = _lib.Model(spec, device=local_rank)
+    theta = synth.random_theta(spec, V, seed=synth.SEED_THETA + rank, bad_frac=0.01)
+    h_theta = torch.from_numpy(np.ascontiguousarray(theta.T)).pin_memory()       # SoA [d][V], pinned
+    h_out = torch.empty(V, dtype=torch.float64).pin_memory()
+    d_theta = h_theta.to(dev)
+    d_out = torch.empty(V, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        model.loglike_ptr(d_theta.data_ptr(), V, V, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+
+    def step_host():
+        model.loglike_ptr(h_theta.data_ptr(), V, V, h_out.data_ptr(), _lib.CC_MEM_HOST, 0)
+
+    # ---------------------------------------------------------------- device-resident leg (value)
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    # per-launch kernel time (CUDA events on the launching stream, recorded inside cc_loglike_batch)
+    for _ in range(3):
+        step_device()
+        torch.cuda.synchronize()
+        kernel_ms.append(model.last_kernel_ms()[0])
+    kern_ms = float(np.mean(kernel_ms))
+    value = V * world * args.steps / (ms_total * 1e-3)
+    ll = d_out.cpu().numpy()
+    full_frac = float(np.mean(ll != _lib.CC_OVERFLO_LOGLIKE))
+
+    # ---------------------------------------------------------------- end-to-end leg (host buffers through the C ABI)
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(2, args.steps // 2)
+    wall0 = time.perf_counter()
+    t0.record()
+    for _ in range(e2e_steps):
+        step_host()
+    t1.record()
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - wall0)
+    e2e_value = V * world * e2e_steps / wall
+    assert np.array_equal(h_out.numpy(), ll), "host path and device path must agree bit for bit"
+
+    # ---------------------------------------------------------------- MCMC leg (configs[2]: 64 chains x 50 rungs per GPU)
+    mcmc = None
+    if args.mcmc_iters > 0:
+        chains, rungs = truth["chains"], truth["rungs"]
+        init = np.tile(synth.true_theta(spec, truth), (chains, 1))
+        burn = args.mcmc_iters + 8
+        mc = _lib.Mcmc(model, burnin=burn, samples=0, rungs=rungs, chains=chains, chain_offset=rank * chains, seed=synth.SEED_MCMC,
+                       record_rungs=False, init=init)
+        mc.advance(5)
+        barrier()
+        m0 = time.perf_counter()
+        mc.advance(args.mcmc_iters)
+        torch.cuda.synchronize()
+        mdt = max_over_ranks(time.perf_counter() - m0)
+        barrier()
+        particles = chains * rungs * world
+        mcmc = {"iter_per_sec_all_chains_x_rungs": particles * args.mcmc_iters / mdt, "chains_per_gpu": chains, "rungs": rungs,
+                "iterations_timed": args.mcmc_iters, "loglike_evals_per_sec": particles * args.mcmc_iters * d / mdt,
+                "ms_per_iteration": mdt / args.mcmc_iters * 1e3, "workload": "cfg3: 64 chains x 50 rungs per GPU, d=34"}
+        mc.close()
+
+    # ---------------------------------------------------------------- roofline + CPU baseline (rank 0)
+    if rank == 0:
+        peak_tf, _ = _lib.fp64_peak_probe(local_rank, 8192)
+        falg = f_alg(spec)
+        flops_per_launch = falg * V * full_frac
+        achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = (8 * d + 8) * V
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+            "kernel": "loglike_batch_kernel", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
+            "peak_source": "cc_fp64_peak_probe (register-resident DFMA chains, measured live in this run; MEASURED_PEAKS.json has no FP64 entry)",
+            "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, n, dt = cpu_reference_rate(spec, theta, args.cpu_seconds, cores)
+            from oracle.oracle import Oracle
+            chk = Oracle(spec).loglike(theta[:n], nthreads=cores)
+            bad = (chk == _lib.CC_OVERFLO_LOGLIKE) | (ll[:n] == _lib.CC_OVERFLO_LOGLIKE)
+            assert np.array_equal(chk[bad], ll[:n][bad])
+            rel = float(np.max(np.abs(chk[~bad] - ll[:n][~bad]) / np.abs(chk[~bad])))
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "first %d of the step's vectors, %.1f s, %d threads (g++ -O2 restatement of the reference; the reference "
+                             "itself needs R/Rcpp/libRmath, absent here)" % (n, dt, cores),
+                   "max_rel_err_gpu_vs_cpu": rel}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "cfg5: likelihood-only, 10 age bands x 300 days x 5 knots x 3 serosurveys, binomial (d=34)",
+                       "vectors_per_gpu_per_step": V, "layout": "SoA theta[d][V]", "l2": "inputs larger than L2 (%.0f MB per step)" % (d * V * 8 / 1e6),
+                       "full_eval_fraction": full_frac},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": d * V * 8, "d2h_bytes_per_step": V * 8, "steps": e2e_steps},
+            "gpu_launches": args.steps,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "mcmc": mcmc,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,853 @@
+// covidcurve_b200.cu - kernels + C ABI (include/covidcurve_b200.h) of the B200-native COVIDCurve hot path.
+//
+// Built for sm_100a only (see __graft_entry__.build()).  There is no CPU fallback anywhere in this file: every
+// compute entry point needs a CUDA device and returns CC_E_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/covidcurve_b200.h"
+#include "cc_eval.cuh"
+#include "cc_mcmc_dev.cuh"
+#include "cc_model.cuh"
+
+using namespace ccdev;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CC_CUDA(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      return fail(CC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
+  } while (0)
+
+extern "C" const char* cc_last_error(void) { return g_err.c_str(); }
+extern "C" int cc_abi_version(void) { return CC_ABI_VERSION; }
+extern "C" int cc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+constexpr int kEvalThreads = 128;
+
+// One CTA per parameter vector; theta is structure-of-arrays [d][ld].
+__global__ void __launch_bounds__(kEvalThreads) loglike_batch_kernel(const KModel m, const double* __restrict__ theta,
+                                                                     long long n, long long ld, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EvalSmem sm = carve_smem(smem_raw, m.d, m.T, m.M);
+  for (long long v = blockIdx.x; v < n; v += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < m.d; i += blockDim.x) sm.p[i] = theta[(long long)i * ld + v];
+    __syncthreads();
+    const double ll = block_loglike(m, sm);
+    if (threadIdx.x == 0) out[v] = ll;
+  }
+}
+
+// One thread per parameter vector (the prior is d cheap terms).
+__global__ void logprior_batch_kernel(const KModel m, const double* __restrict__ theta, long long n, long long ld,
+                                      double* __restrict__ out) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  out[v] = thread_logprior(m, theta + v, (int)ld);
+}
+
+// Intermediates for the post-processing re-entry points (R/summarize_plot.R:276-884).
+__global__ void __launch_bounds__(kEvalThreads) curves_kernel(const KModel m, const double* __restrict__ theta, long long n,
+                                                              long long ld, double* __restrict__ o_infxn,
+                                                              double* __restrict__ o_ne, double* __restrict__ o_auc,
+                                                              double* __restrict__ o_sero) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // curves need the hazard over all T days (summarize_plot.R:733-771), so carve with M = T
+  KModel mc = m;
+  mc.M = m.T;
+  mc.S = 0;  // no survey sums needed
+  EvalSmem sm = carve_smem(smem_raw, m.d, m.T, m.T);
+  const int T = m.T, A = m.A;
+  for (long long v = blockIdx.x; v < n; v += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < m.d; i += blockDim.x) sm.p[i] = theta[(long long)i * ld + v];
+    __syncthreads();
+    const double ll = block_loglike(mc, sm);
+    __syncthreads();
+    const bool ok = sm.sc->nodex_pass && (ll != -CC_OVERFLO || true);
+    // an invalid knot order leaves no curve: report NaN like an aborted evaluation would
+    const bool have = sm.sc->nodex_pass != 0;
+    (void)ok;
+    if (o_ne)
+      for (int a = threadIdx.x; a < A; a += blockDim.x) o_ne[v * A + a] = sm.sc->ne[a];
+    if (o_infxn)
+      for (int i = threadIdx.x; i < T; i += blockDim.x) o_infxn[v * T + i] = have ? sm.infxn[i] : d_nan();
+    const bool conv_ok = have && sm.sc->popn_pass;
+    if (o_auc)
+      for (int i = threadIdx.x; i < T; i += blockDim.x) o_auc[v * T + i] = conv_ok ? sm.auc[i] : d_nan();
+    if (o_sero) {
+      // sero_full[j] = sum_{i<=j} infxn[i] * haz[j-i]
+      if (conv_ok) {
+        __syncthreads();
+        causal_conv(sm.infxn, sm.haz, T, sm.tmp1);
+        __syncthreads();
+      }
+      for (int i = threadIdx.x; i < T; i += blockDim.x) o_sero[v * T + i] = conv_ok ? sm.tmp1[i] : d_nan();
+    }
+  }
+}
+
+// ---- MCMC kernels
+// initial state: phi, loglike, logprior of every particle
+__global__ void __launch_bounds__(kEvalThreads) mcmc_init_kernel(const KModel m, const McmcState s) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EvalSmem sm = carve_smem(smem_raw, m.d, m.T, m.M);
+  const int P = s.n_chains * s.rungs;
+  for (int p = blockIdx.x; p < P; p += gridDim.x) {
+    __syncthreads();
+    double* th = s.theta + (size_t)p * m.d;
+    for (int i = threadIdx.x; i < m.d; i += blockDim.x) {
+      const double t = th[i];
+      sm.p[i] = t;
+      const double lo = m.pmin[i], hi = m.pmax[i];
+      s.phi[(size_t)p * m.d + i] = theta_to_phi(trans_type(lo, hi), t, lo, hi);
+    }
+    __syncthreads();
+    const double ll = block_loglike(m, sm);
+    __syncthreads();
+    const double lp = block_logprior(m, sm.p, sm.red);
+    if (threadIdx.x == 0) {
+      s.ll[p] = ll;
+      s.lp[p] = lp;
+    }
+  }
+}
+
+// One sweep of d single-site Metropolis-Hastings updates for every (chain, rung); one CTA per particle.
+// `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
+__global__ void __launch_bounds__(kEvalThreads) mcmc_sweep_kernel(const KModel m, const McmcState s, int iteration) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EvalSmem sm = carve_smem(smem_raw, m.d, m.T, m.M);
+  __shared__ double sh_prop[4];  // theta', phi', adj, u
+  const int d = m.d;
+  const int P = s.n_chains * s.rungs;
+  const bool adapt = s.adapt_in_sampling || iteration <= s.burnin;
+  for (int b = blockIdx.x; b < P; b += gridDim.x) {
+    const int c = b / s.rungs, r = b - c * s.rungs;
+    const int pid = s.at_rung[b];            // particle (within chain) sitting at rung position r
+    const int p = c * s.rungs + pid;
+    const int slot = s.bw_per_particle ? p : b;
+    const double beta = s.beta[r];
+    double* th = s.theta + (size_t)p * d;
+    double* ph = s.phi + (size_t)p * d;
+    double* bw = s.bw + (size_t)slot * d;
+    int* bwi = s.bw_index + (size_t)slot * d;
+    unsigned int* macc = s.move_acc + (size_t)b * d;
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += blockDim.x) sm.p[i] = th[i];
+    double ll = s.ll[p], lp = s.lp[p];
+    __syncthreads();
+    for (int i = 0; i < d; i++) {
+      if (threadIdx.x == 0) {
+        const ccrng::Draw dr = ccrng::draw(s.seed, ccrng::kStreamMove, (uint32_t)(s.chain_offset + c), (uint32_t)pid,
+                                           (uint32_t)iteration, (uint32_t)i);
+        const double lo = m.pmin[i], hi = m.pmax[i];
+        const int tt = trans_type(lo, hi);
+        const double php = ph[i] + bw[i] * dr.z;
+        const double thp = phi_to_theta(tt, php, lo, hi);
+        sh_prop[0] = thp;
+        sh_prop[1] = php;
+        sh_prop[2] = mh_adjust(tt, sm.p[i], thp, lo, hi);
+        sh_prop[3] = dr.u;
+      }
+      __syncthreads();
+      const double th_old = sm.p[i];
+      __syncthreads();
+      if (threadIdx.x == 0) sm.p[i] = sh_prop[0];
+      __syncthreads();
+      const double llp = block_loglike(m, sm);
+      __syncthreads();
+      const double lpp = block_logprior(m, sm.p, sm.red);
+      const double mh = beta * (llp - ll) + (lpp - lp) + sh_prop[2];
+      const bool acc = log(sh_prop[3]) < mh;  // block-uniform: every thread holds the same values
+      if (acc) {
+        ll = llp;
+        lp = lpp;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (acc) {
+          ph[i] = sh_prop[1];
+          macc[i] += 1u;
+        } else {
+          sm.p[i] = th_old;
+        }
+        if (adapt) {
+          // Robbins-Monro on log(bw) towards a 0.234 acceptance rate
+          const double step = acc ? (1.0 - 0.234) : -0.234;
+          bw[i] = exp(log(bw[i]) + step / sqrt((double)bwi[i]));
+          bwi[i] += 1;
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < d; i += blockDim.x) th[i] = sm.p[i];
+    if (threadIdx.x == 0) {
+      s.ll[p] = ll;
+      s.lp[p] = lp;
+    }
+  }
+}
+
+// Metropolis coupling (sequential over adjacent rung pairs, like drjacoby) + recording of this iteration.
+// One CTA per chain.  `row` < 0: do not record.  `do_swap` = 0 for the initial state.
+__global__ void mcmc_swap_record_kernel(const KModel m, const McmcState s, int iteration, long long row, int do_swap) {
+  const int c = blockIdx.x;
+  const int R = s.rungs, d = m.d;
+  int* at = s.at_rung + (size_t)c * R;
+  if (threadIdx.x == 0 && do_swap && s.coupling_on && R > 1) {
+    const bool sampling = iteration > s.burnin;
+    for (int k = 0; k < R - 1; k++) {
+      const int p1 = c * R + at[k], p2 = c * R + at[k + 1];
+      const double l1 = s.ll[p1], l2 = s.ll[p2];
+      const double b1 = s.beta[k], b2 = s.beta[k + 1];
+      const double a = (l2 - l1) * (b1 - b2);
+      const ccrng::Draw dr = ccrng::draw(s.seed, ccrng::kStreamSwap, (uint32_t)(s.chain_offset + c), (uint32_t)k,
+                                         (uint32_t)iteration, 0u);
+      const bool acc = log(dr.u) < a;
+      if (sampling) s.swap_try[(size_t)c * (R - 1) + k] += 1u;
+      if (acc) {
+        const int t = at[k];
+        at[k] = at[k + 1];
+        at[k + 1] = t;
+        if (sampling) s.swap_acc[(size_t)c * (R - 1) + k] += 1u;
+      }
+    }
+  }
+  __syncthreads();
+  if (row < 0) return;
+  for (int q = 0; q < s.n_rec_rungs; q++) {
+    const int r = s.record_all ? q : s.cold_pos;
+    const int p = c * R + at[r];
+    const size_t o = ((size_t)c * s.n_rec_rungs + q) * (size_t)s.rows_cap + (size_t)row;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) s.rec_theta[o * d + i] = s.theta[(size_t)p * d + i];
+    if (threadIdx.x == 0) {
+      s.rec_ll[o] = s.ll[p];
+      s.rec_lp[o] = s.lp[p];
+    }
+  }
+}
+
+// ---- FP64 FMA peak probe: 8 independent register-resident DFMA chains per thread
+__global__ void fp64_probe_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double sum = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (sum == 123.456) out[0] = sum;  // keep the chains alive without a store in the common case
+}
+
+// ------------------------------------------------------------------------------------------------ model
+static double host_stirlerr(double n) {
+  const double S0 = 0.083333333333333333333, S1 = 0.00277777777777777777778, S2 = 0.00079365079365079365079365,
+               S3 = 0.000595238095238095238095238, S4 = 0.0008417508417508417508417508;
+  if (n <= 15.0) {
+    double nn = n + n;
+    if (nn == (double)(int)nn) return h_sferr_halves[(int)nn];
+    return std::lgamma(n + 1.) - (n + 0.5) * std::log(n) + n - CC_LN_SQRT_2PI;
+  }
+  double nn = n * n;
+  if (n > 500) return (S0 - S1 / nn) / n;
+  if (n > 80) return (S0 - (S1 - S2 / nn) / nn) / n;
+  if (n > 35) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+  return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+template <typename T>
+static int upload(cc_model* m, const std::vector<T>& h, const T** dptr) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  CC_CUDA(cudaMalloc(&p, bytes));
+  m->dev_allocs.push_back(p);
+  if (!h.empty()) CC_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dptr = static_cast<const T*>(p);
+  return CC_OK;
+}
+
+static bool idx_ok(int i, int d) { return i >= 0 && i < d; }
+
+extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** out) {
+  if (!de || !out) return fail(CC_E_INVALID, "cc_model_create: null argument");
+  *out = nullptr;
+  if (de->abi_version != CC_ABI_VERSION) return fail(CC_E_INVALID, "cc_model_create: abi_version mismatch");
+  const int d = de->n_params, A = de->n_strata, K = de->n_knots, T = de->days_obsd, S = de->n_sero_obs, M = de->max_seroday_obsd;
+  if (d < 1 || d > CC_MAX_PARAMS) return fail(CC_E_INVALID, "n_params out of range [1, CC_MAX_PARAMS]");
+  if (A < 1 || A > CC_MAX_STRATA) return fail(CC_E_INVALID, "n_strata out of range [1, CC_MAX_STRATA]");
+  if (K < 3 || K > CC_MAX_KNOTS) return fail(CC_E_INVALID, "n_knots out of range [3, CC_MAX_KNOTS]");
+  if (T < 1 || T > CC_MAX_DAYS) return fail(CC_E_INVALID, "days_obsd out of range [1, CC_MAX_DAYS]");
+  if (S < 1 || S > CC_MAX_SEROSURVEYS) return fail(CC_E_INVALID, "n_sero_obs out of range [1, CC_MAX_SEROSURVEYS]");
+  if (M < 1 || M > T) return fail(CC_E_INVALID, "max_seroday_obsd must be in [1, days_obsd] (the reference reads infxn_spline[0..M-1])");
+  if (!de->demog || !de->obs_deaths || !de->prop_strata_obs_deaths || !de->sero_a || !de->sero_b || !de->sero_survey_start ||
+      !de->sero_survey_end || !de->idx_knots || !de->idx_infxn || !de->idx_ifr || !de->pmin || !de->pmax || !de->prior_family ||
+      !de->prior_p1 || !de->prior_p2)
+    return fail(CC_E_INVALID, "cc_model_create: null array in descriptor");
+  if (A > 1 && !de->idx_noise) return fail(CC_E_INVALID, "idx_noise is required when n_strata > 1");
+  for (int s = 0; s < S; s++)
+    if (de->sero_survey_start[s] < 1 || de->sero_survey_end[s] < de->sero_survey_start[s] || de->sero_survey_end[s] > M)
+      return fail(CC_E_INVALID, "serosurvey windows must satisfy 1 <= start <= end <= max_seroday_obsd");
+  bool ok = idx_ok(de->idx_sens, d) && idx_ok(de->idx_spec, d) && idx_ok(de->idx_sero_con_rate, d) && idx_ok(de->idx_mod, d) &&
+            idx_ok(de->idx_sod, d);
+  if (de->account_serorev) ok = ok && idx_ok(de->idx_sero_rev_shape, d) && idx_ok(de->idx_sero_rev_scale, d);
+  for (int i = 0; i < K - 1; i++) ok = ok && idx_ok(de->idx_knots[i], d);
+  for (int i = 0; i < K; i++) ok = ok && idx_ok(de->idx_infxn[i], d);
+  for (int a = 0; a < A; a++) ok = ok && idx_ok(de->idx_ifr[a], d);
+  if (A > 1)
+    for (int a = 0; a < A; a++) ok = ok && idx_ok(de->idx_noise[a], d);
+  if (de->reparam_knots) ok = ok && idx_ok(de->idx_rel_knot, d);
+  if (de->reparam_infxn) ok = ok && idx_ok(de->idx_rel_infxn, d);
+  if (de->reparam_ifr) ok = ok && idx_ok(de->idx_max_ma, d);
+  for (int j = 0; j < 3; j++) ok = ok && (de->jac_rows[j] < d);
+  if (!ok) return fail(CC_E_INVALID, "role map index out of range");
+  for (int i = 0; i < d; i++)
+    if (de->prior_family[i] < CC_PRIOR_NONE || de->prior_family[i] > CC_PRIOR_DBETA) return fail(CC_E_INVALID, "unknown prior family");
+
+  int ndev = cc_device_count();
+  if (ndev <= 0) return fail(CC_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(CC_E_INVALID, "device index out of range");
+  CC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CC_CUDA(cudaGetDeviceProperties(&prop, device));
+
+  cc_model* m = new (std::nothrow) cc_model();
+  if (!m) return fail(CC_E_NOMEM, "out of host memory");
+  m->device = device;
+  m->sm_count = prop.multiProcessorCount;
+  KModel& k = m->k;
+  k.d = d; k.A = A; k.K = K; k.T = T; k.S = S; k.M = M;
+  k.rcensor_day = de->rcensor_day;
+  k.serorev = de->account_serorev ? 1 : 0;
+  k.binomial = de->binomial_likelihood ? 1 : 0;
+  k.reparam_ifr = de->reparam_ifr ? 1 : 0;
+  k.reparam_knots = de->reparam_knots ? 1 : 0;
+  k.reparam_infxn = de->reparam_infxn ? 1 : 0;
+  k.idx_sens = de->idx_sens; k.idx_spec = de->idx_spec; k.idx_rate = de->idx_sero_con_rate;
+  k.idx_shape = de->account_serorev ? de->idx_sero_rev_shape : -1;
+  k.idx_scale = de->account_serorev ? de->idx_sero_rev_scale : -1;
+  k.idx_mod = de->idx_mod; k.idx_sod = de->idx_sod;
+  k.idx_rel_knot = de->reparam_knots ? de->idx_rel_knot : -1;
+  k.idx_rel_infxn = de->reparam_infxn ? de->idx_rel_infxn : -1;
+  k.idx_max_ma = de->reparam_ifr ? de->idx_max_ma : -1;
+  for (int i = 0; i < K - 1; i++) k.idx_knots[i] = (short)de->idx_knots[i];
+  for (int i = 0; i < K; i++) k.idx_infxn[i] = (short)de->idx_infxn[i];
+  for (int a = 0; a < A; a++) {
+    k.idx_ifr[a] = (short)de->idx_ifr[a];
+    k.idx_noise[a] = (short)(A > 1 ? de->idx_noise[a] : 0);
+    k.demog[a] = (int)de->demog[a];  // binomial.cpp:10 (Rcpp::as<std::vector<int>>)
+  }
+  // L2 probabilities are data-only: paobsd[a] / running paobsd_sum (binomial.cpp:238-250)
+  {
+    double psum = 0.0;
+    for (int a = 0; a < A; a++) psum += de->prop_strata_obs_deaths[a];
+    for (int a = 0; a < A; a++) {
+      k.l2_prob[a] = de->prop_strata_obs_deaths[a] / psum;
+      psum -= de->prop_strata_obs_deaths[a];
+    }
+  }
+  for (int s = 0; s < S; s++) {
+    k.sero_start[s] = de->sero_survey_start[s];
+    k.sero_end[s] = de->sero_survey_end[s];
+  }
+  for (int j = 0; j < 3; j++) {
+    k.jac_rows[j] = de->jac_rows[j];
+    k.jac_counts[j] = de->jac_counts[j];
+  }
+  if (!de->reparam_ifr) k.jac_rows[0] = -1;
+  if (!de->reparam_knots) k.jac_rows[1] = -1;
+  if (!de->reparam_infxn) k.jac_rows[2] = -1;
+
+  std::vector<int> obsd(T);
+  std::vector<double> pois_c(T), lgx1(T);
+  for (int i = 0; i < T; i++) {
+    obsd[i] = (int)de->obs_deaths[i];  // binomial.cpp:204
+    const double x = (double)obsd[i];
+    pois_c[i] = (x > 0) ? (-0.5 * std::log(CC_2PI * x) - host_stirlerr(x)) : 0.0;
+    lgx1[i] = (x >= 0) ? std::lgamma(x + 1.0) : 0.0;
+  }
+  std::vector<double> sa(de->sero_a, de->sero_a + (size_t)S * A), sb(de->sero_b, de->sero_b + (size_t)S * A);
+  std::vector<double> pmin(de->pmin, de->pmin + d), pmax(de->pmax, de->pmax + d);
+  std::vector<int> fam(de->prior_family, de->prior_family + d);
+  std::vector<double> p1(de->prior_p1, de->prior_p1 + d), p2(de->prior_p2, de->prior_p2 + d);
+  int rc = CC_OK;
+  if ((rc = upload(m, obsd, &k.obsd)) || (rc = upload(m, pois_c, &k.pois_c)) || (rc = upload(m, lgx1, &k.lgx1)) ||
+      (rc = upload(m, sa, &k.sero_a)) || (rc = upload(m, sb, &k.sero_b)) || (rc = upload(m, pmin, &k.pmin)) ||
+      (rc = upload(m, pmax, &k.pmax)) || (rc = upload(m, fam, &k.prior_family)) || (rc = upload(m, p1, &k.prior_p1)) ||
+      (rc = upload(m, p2, &k.prior_p2))) {
+    cc_model_destroy(m);
+    return rc;
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&m->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
+  for (int q = 0; q < 2 && e == cudaSuccess; q++) e = cudaEventCreateWithFlags(&m->ev_stage[q], cudaEventDisableTiming);
+  // opt in to large dynamic shared memory once (T up to CC_MAX_DAYS needs > 48 KB)
+  const size_t smem = eval_smem_bytes(d, T, T);
+  if (e == cudaSuccess && smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(loglike_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(curves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  if (e != cudaSuccess) {
+    cc_model_destroy(m);
+    return fail(CC_E_CUDA, std::string("cc_model_create: ") + cudaGetErrorString(e));
+  }
+  *out = m;
+  return CC_OK;
+}
+
+extern "C" void cc_model_destroy(cc_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (void* p : m->dev_allocs) cudaFree(p);
+  if (m->d_stage) cudaFree(m->d_stage);
+  if (m->d_out) cudaFree(m->d_out);
+  if (m->h_pin) cudaFreeHost(m->h_pin);
+  for (int q = 0; q < 2; q++)
+    if (m->ev_stage[q]) cudaEventDestroy(m->ev_stage[q]);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->stream2) cudaStreamDestroy(m->stream2);
+  delete m;
+}
+
+// ------------------------------------------------------------------------------------------------ batch calls
+static int launch_loglike(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st) {
+  const KModel& k = m->k;
+  const size_t smem = eval_smem_bytes(k.d, k.T, k.M);
+  const long long grid = std::min<long long>(n, 0x7fffffffLL);
+  loglike_batch_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(k, d_theta, n, ld, d_out);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+static int launch_logprior(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st) {
+  const int bs = 128;
+  const long long grid = (n + bs - 1) / bs;
+  logprior_batch_kernel<<<(unsigned)grid, bs, 0, st>>>(m->k, d_theta, n, ld, d_out);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+static int ensure_stage(cc_model* m, size_t theta_bytes, size_t out_bytes) {
+  if (m->d_stage_bytes < theta_bytes) {
+    if (m->d_stage) cudaFree(m->d_stage);
+    m->d_stage = nullptr;
+    m->d_stage_bytes = 0;
+    CC_CUDA(cudaMalloc((void**)&m->d_stage, theta_bytes));
+    m->d_stage_bytes = theta_bytes;
+  }
+  if (m->d_out_bytes < out_bytes) {
+    if (m->d_out) cudaFree(m->d_out);
+    m->d_out = nullptr;
+    m->d_out_bytes = 0;
+    CC_CUDA(cudaMalloc((void**)&m->d_out, out_bytes));
+    m->d_out_bytes = out_bytes;
+  }
+  return CC_OK;
+}
+
+typedef int (*launch_fn)(cc_model*, const double*, long long, long long, double*, cudaStream_t);
+
+// Host-buffer path: column chunks are copied H2D (2-D copy: d rows of `chunk` doubles), evaluated and copied back,
+// double-buffered over two streams so that copies overlap the kernel.  Pinned caller memory gives true overlap;
+// pageable memory still works (the driver stages it).
+static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long long n, long long ld, double* out) {
+  const int d = m->k.d;
+  const long long kChunk = 1 << 16;
+  const long long chunk = std::min<long long>(n, kChunk);
+  int rc = ensure_stage(m, (size_t)2 * d * chunk * sizeof(double), (size_t)2 * chunk * sizeof(double));
+  if (rc) return rc;
+  cudaStream_t st[2] = {m->stream, m->stream2};
+  CC_CUDA(cudaEventRecord(m->ev0, st[0]));
+  m->last_launches = 0;
+  int q = 0;
+  for (long long c0 = 0; c0 < n; c0 += chunk, q ^= 1) {
+    const long long cn = std::min(chunk, n - c0);
+    double* dth = m->d_stage + (size_t)q * d * chunk;
+    double* dout = m->d_out + (size_t)q * chunk;
+    CC_CUDA(cudaMemcpy2DAsync(dth, (size_t)chunk * sizeof(double), theta + c0, (size_t)ld * sizeof(double),
+                              (size_t)cn * sizeof(double), (size_t)d, cudaMemcpyHostToDevice, st[q]));
+    rc = fn(m, dth, cn, chunk, dout, st[q]);
+    if (rc) return rc;
+    m->last_launches++;
+    CC_CUDA(cudaMemcpyAsync(out + c0, dout, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost, st[q]));
+  }
+  CC_CUDA(cudaEventRecord(m->ev_stage[1], st[1]));
+  CC_CUDA(cudaStreamWaitEvent(st[0], m->ev_stage[1], 0));
+  CC_CUDA(cudaEventRecord(m->ev1, st[0]));
+  CC_CUDA(cudaStreamSynchronize(st[0]));
+  float ms = 0.f;
+  CC_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+  m->last_ms = ms;
+  return CC_OK;
+}
+
+static int batch_call(cc_model* m, launch_fn fn, const double* theta, int64_t n, int64_t ld, double* out, int mem, void* stream,
+                      const char* who) {
+  if (!m || !theta || !out) return fail(CC_E_INVALID, std::string(who) + ": null argument");
+  if (n < 0 || ld < n) return fail(CC_E_INVALID, std::string(who) + ": need 0 <= n <= ld");
+  if (n == 0) return CC_OK;
+  CC_CUDA(cudaSetDevice(m->device));
+  if (mem == CC_MEM_DEVICE) {
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    CC_CUDA(cudaEventRecord(m->ev0, st));
+    int rc = fn(m, theta, n, ld, out, st);
+    if (rc) return rc;
+    CC_CUDA(cudaEventRecord(m->ev1, st));
+    m->last_launches = 1;
+    m->last_ms = -1.0;  // resolved lazily by cc_last_kernel_ms
+    return CC_OK;
+  }
+  if (mem != CC_MEM_HOST) return fail(CC_E_INVALID, std::string(who) + ": mem must be CC_MEM_HOST or CC_MEM_DEVICE");
+  return run_host_batch(m, fn, theta, n, ld, out);
+}
+
+extern "C" int cc_loglike_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* out, int mem, void* stream) {
+  return batch_call(m, launch_loglike, theta, n, ld, out, mem, stream, "cc_loglike_batch");
+}
+
+extern "C" int cc_logprior_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* out, int mem, void* stream) {
+  return batch_call(m, launch_logprior, theta, n, ld, out, mem, stream, "cc_logprior_batch");
+}
+
+extern "C" int cc_loglike(cc_model* m, const double* params, int /*param_i: ignored like binomial.cpp:7*/, double* out) {
+  return batch_call(m, launch_loglike, params, 1, 1, out, CC_MEM_HOST, nullptr, "cc_loglike");
+}
+
+extern "C" int cc_logprior(cc_model* m, const double* params, int /*param_i*/, double* out) {
+  return batch_call(m, launch_logprior, params, 1, 1, out, CC_MEM_HOST, nullptr, "cc_logprior");
+}
+
+extern "C" int cc_last_kernel_ms(cc_model* m, double* ms, int32_t* launches) {
+  if (!m) return fail(CC_E_INVALID, "cc_last_kernel_ms: null model");
+  if (m->last_ms < 0) {
+    CC_CUDA(cudaEventSynchronize(m->ev1));
+    float f = 0.f;
+    CC_CUDA(cudaEventElapsedTime(&f, m->ev0, m->ev1));
+    m->last_ms = f;
+  }
+  if (ms) *ms = m->last_ms;
+  if (launches) *launches = m->last_launches;
+  return CC_OK;
+}
+
+extern "C" int cc_curves_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* infxn, double* ne, double* auc,
+                               double* sero_full) {
+  if (!m || !theta) return fail(CC_E_INVALID, "cc_curves_batch: null argument");
+  if (n < 0 || ld < n) return fail(CC_E_INVALID, "cc_curves_batch: need 0 <= n <= ld");
+  if (n == 0) return CC_OK;
+  CC_CUDA(cudaSetDevice(m->device));
+  const KModel& k = m->k;
+  const int d = k.d, T = k.T, A = k.A;
+  double *dth = nullptr, *di = nullptr, *dn = nullptr, *da = nullptr, *ds = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(dth); cudaFree(di); cudaFree(dn); cudaFree(da); cudaFree(ds);
+  };
+  cudaError_t e = cudaMalloc((void**)&dth, (size_t)d * n * sizeof(double));
+  if (e == cudaSuccess && infxn) e = cudaMalloc((void**)&di, (size_t)n * T * sizeof(double));
+  if (e == cudaSuccess && ne) e = cudaMalloc((void**)&dn, (size_t)n * A * sizeof(double));
+  if (e == cudaSuccess && auc) e = cudaMalloc((void**)&da, (size_t)n * T * sizeof(double));
+  if (e == cudaSuccess && sero_full) e = cudaMalloc((void**)&ds, (size_t)n * T * sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(dth, (size_t)n * sizeof(double), theta, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), (size_t)d,
+                          cudaMemcpyHostToDevice, m->stream);
+  if (e == cudaSuccess) {
+    const size_t smem = eval_smem_bytes(d, T, T);
+    curves_kernel<<<(unsigned)std::min<long long>(n, 65535LL * 16), kEvalThreads, smem, m->stream>>>(k, dth, n, n, di, dn, da, ds);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && infxn) e = cudaMemcpyAsync(infxn, di, (size_t)n * T * sizeof(double), cudaMemcpyDeviceToHost, m->stream);
+  if (e == cudaSuccess && ne) e = cudaMemcpyAsync(ne, dn, (size_t)n * A * sizeof(double), cudaMemcpyDeviceToHost, m->stream);
+  if (e == cudaSuccess && auc) e = cudaMemcpyAsync(auc, da, (size_t)n * T * sizeof(double), cudaMemcpyDeviceToHost, m->stream);
+  if (e == cudaSuccess && sero_full) e = cudaMemcpyAsync(sero_full, ds, (size_t)n * T * sizeof(double), cudaMemcpyDeviceToHost, m->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  cleanup();
+  if (e != cudaSuccess) return fail(CC_E_CUDA, std::string("cc_curves_batch: ") + cudaGetErrorString(e));
+  return CC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MCMC host side
+struct cc_mcmc {
+  cc_model* m = nullptr;
+  McmcState s{};
+  std::vector<void*> allocs;
+  std::vector<double> beta;
+  std::vector<int32_t> rec_iter;  // iteration number of every recorded row
+  long long iteration = 0;        // iterations done (1 after create)
+  long long rows = 0;
+  long long evals = 0;
+  size_t smem = 0;
+};
+
+template <typename T>
+static int dalloc(cc_mcmc* s, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  CC_CUDA(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  s->allocs.push_back(q);
+  if (zero) CC_CUDA(cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  *p = static_cast<T*>(q);
+  return CC_OK;
+}
+
+extern "C" void cc_mcmc_destroy(cc_mcmc* s) {
+  if (!s) return;
+  cudaSetDevice(s->m->device);
+  for (void* p : s->allocs) cudaFree(p);
+  delete s;
+}
+
+static int record_and_swap(cc_mcmc* r, int iteration, int do_swap) {
+  McmcState& s = r->s;
+  const int thin = s.thin <= 1 ? 1 : s.thin;
+  long long row = -1;
+  if (iteration % thin == 0 && r->rows < s.rows_cap) row = r->rows;
+  if (!(do_swap && s.coupling_on && s.rungs > 1) && row < 0) return CC_OK;
+  const int bs = std::min(128, std::max(32, ((s.d + 31) / 32) * 32));
+  mcmc_swap_record_kernel<<<s.n_chains, bs, 0, r->m->stream>>>(r->m->k, s, iteration, row, do_swap);
+  CC_CUDA(cudaGetLastError());
+  if (row >= 0) {
+    r->rec_iter.push_back(iteration);
+    r->rows++;
+  }
+  return CC_OK;
+}
+
+extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out) {
+  if (!m || !o || !out) return fail(CC_E_INVALID, "cc_mcmc_create: null argument");
+  *out = nullptr;
+  if (o->burnin < 1 || o->samples < 0 || o->rungs < 1 || o->n_chains < 1 || o->chain_offset < 0)
+    return fail(CC_E_INVALID, "cc_mcmc_create: need burnin >= 1, samples >= 0, rungs >= 1, n_chains >= 1");
+  if (!o->init && !o->init_default) return fail(CC_E_INVALID, "cc_mcmc_create: init or init_default is required");
+  CC_CUDA(cudaSetDevice(m->device));
+  const int d = m->k.d, R = o->rungs, C = o->n_chains;
+  const size_t P = (size_t)R * C;
+
+  // thermodynamic powers: equally spaced on [0, 1] raised to GTI_pow; a single rung is the cold chain (power 1)
+  std::vector<double> beta(R);
+  if (o->beta_manual) {
+    for (int r = 0; r < R; r++) beta[r] = o->beta_manual[r];
+  } else if (R == 1) {
+    beta[0] = 1.0;
+  } else {
+    for (int r = 0; r < R; r++) beta[r] = std::pow((double)r / (double)(R - 1), o->GTI_pow);
+  }
+  const bool cold_last = o->beta_manual ? true : (o->cold_rung_last != 0);
+  if (!o->beta_manual && !cold_last) std::reverse(beta.begin(), beta.end());
+  int cold_pos = 0;
+  for (int r = 0; r < R; r++)
+    if (beta[r] >= beta[cold_pos]) cold_pos = r;
+  if (!cold_last)
+    for (int r = R - 1; r >= 0; r--)
+      if (beta[r] >= beta[cold_pos]) cold_pos = r;
+
+  cc_mcmc* r = new (std::nothrow) cc_mcmc();
+  if (!r) return fail(CC_E_NOMEM, "out of host memory");
+  r->m = m;
+  r->beta = beta;
+  McmcState& s = r->s;
+  s.d = d; s.rungs = R; s.n_chains = C; s.chain_offset = o->chain_offset;
+  s.burnin = o->burnin; s.samples = o->samples; s.coupling_on = o->coupling_on ? 1 : 0;
+  s.record_all = o->record_rungs ? 1 : 0;
+  s.thin = o->thin <= 1 ? 1 : o->thin;
+  s.bw_per_particle = o->bw_per_particle ? 1 : 0;
+  s.adapt_in_sampling = o->no_adapt_in_sampling ? 0 : 1;
+  s.seed = o->seed;
+  s.n_rec_rungs = s.record_all ? R : 1;
+  s.cold_pos = cold_pos;
+  s.rows_cap = ((long long)o->burnin + o->samples) / s.thin;
+  if (s.rows_cap < 1) s.rows_cap = 1;
+  int rc = CC_OK;
+  const size_t rec = (size_t)C * s.n_rec_rungs * (size_t)s.rows_cap;
+  if ((rc = dalloc(r, &s.theta, P * d)) || (rc = dalloc(r, &s.phi, P * d)) || (rc = dalloc(r, &s.ll, P)) ||
+      (rc = dalloc(r, &s.lp, P)) || (rc = dalloc(r, &s.bw, P * d)) || (rc = dalloc(r, &s.bw_index, P * d)) ||
+      (rc = dalloc(r, &s.move_acc, P * d)) || (rc = dalloc(r, &s.at_rung, P)) || (rc = dalloc(r, &s.beta, (size_t)R)) ||
+      (rc = dalloc(r, &s.swap_acc, (size_t)C * std::max(R - 1, 1))) || (rc = dalloc(r, &s.swap_try, (size_t)C * std::max(R - 1, 1))) ||
+      (rc = dalloc(r, &s.rec_theta, rec * d, false)) || (rc = dalloc(r, &s.rec_ll, rec, false)) ||
+      (rc = dalloc(r, &s.rec_lp, rec, false))) {
+    cc_mcmc_destroy(r);
+    return rc;
+  }
+  {
+    std::vector<double> th(P * d), bw(P * d, 1.0);
+    std::vector<int> bwi(P * d, 1), at(P);
+    for (int c = 0; c < C; c++)
+      for (int q = 0; q < R; q++) {
+        const double* src = o->init ? o->init + (size_t)c * d : o->init_default;
+        std::copy(src, src + d, th.begin() + ((size_t)c * R + q) * d);
+        at[(size_t)c * R + q] = q;
+      }
+    cudaError_t e = cudaMemcpy(s.theta, th.data(), th.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s.bw, bw.data(), bw.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s.bw_index, bwi.data(), bwi.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s.at_rung, at.data(), at.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s.beta, beta.data(), beta.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cc_mcmc_destroy(r);
+      return fail(CC_E_CUDA, std::string("cc_mcmc_create: ") + cudaGetErrorString(e));
+    }
+  }
+  r->smem = eval_smem_bytes(d, m->k.T, m->k.M);
+  mcmc_init_kernel<<<(unsigned)P, kEvalThreads, r->smem, m->stream>>>(m->k, s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cc_mcmc_destroy(r);
+    return fail(CC_E_CUDA, std::string("mcmc_init_kernel: ") + cudaGetErrorString(e));
+  }
+  r->evals += (long long)P;
+  r->iteration = 1;
+  rc = record_and_swap(r, 1, 0);
+  if (rc == CC_OK) {
+    e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) rc = fail(CC_E_CUDA, std::string("cc_mcmc_create: ") + cudaGetErrorString(e));
+  }
+  if (rc) {
+    cc_mcmc_destroy(r);
+    return rc;
+  }
+  *out = r;
+  return CC_OK;
+}
+
+extern "C" int cc_mcmc_advance(cc_mcmc* r, int32_t n_iter) {
+  if (!r) return fail(CC_E_INVALID, "cc_mcmc_advance: null state");
+  if (n_iter < 0) return fail(CC_E_INVALID, "cc_mcmc_advance: n_iter < 0");
+  cc_model* m = r->m;
+  CC_CUDA(cudaSetDevice(m->device));
+  McmcState& s = r->s;
+  const long long total = (long long)s.burnin + s.samples;
+  const unsigned P = (unsigned)(s.n_chains * s.rungs);
+  for (int k = 0; k < n_iter; k++) {
+    if (r->iteration >= total) return fail(CC_E_STATE, "cc_mcmc_advance: burnin + samples iterations already done");
+    const int it = (int)(r->iteration + 1);
+    mcmc_sweep_kernel<<<P, kEvalThreads, r->smem, m->stream>>>(m->k, s, it);
+    CC_CUDA(cudaGetLastError());
+    r->evals += (long long)P * s.d;
+    int rc = record_and_swap(r, it, 1);
+    if (rc) return rc;
+    r->iteration = it;
+  }
+  CC_CUDA(cudaStreamSynchronize(m->stream));
+  return CC_OK;
+}
+
+extern "C" int64_t cc_mcmc_iterations(const cc_mcmc* s) { return s ? s->iteration : 0; }
+extern "C" int64_t cc_mcmc_rows(const cc_mcmc* s) { return s ? s->rows : 0; }
+extern "C" int64_t cc_mcmc_loglike_evals(const cc_mcmc* s) { return s ? s->evals : 0; }
+
+// recorded draws are stored with a row capacity; fetch compacts to [chains][rec rungs][rows][..]
+extern "C" int cc_mcmc_fetch(cc_mcmc* r, double* theta, double* loglike, double* logprior, int32_t* iteration) {
+  if (!r) return fail(CC_E_INVALID, "cc_mcmc_fetch: null state");
+  CC_CUDA(cudaSetDevice(r->m->device));
+  const McmcState& s = r->s;
+  const size_t groups = (size_t)s.n_chains * s.n_rec_rungs, rows = (size_t)r->rows, cap = (size_t)s.rows_cap, d = (size_t)s.d;
+  CC_CUDA(cudaStreamSynchronize(r->m->stream));
+  if (theta)
+    CC_CUDA(cudaMemcpy2D(theta, rows * d * sizeof(double), s.rec_theta, cap * d * sizeof(double), rows * d * sizeof(double), groups,
+                         cudaMemcpyDeviceToHost));
+  if (loglike)
+    CC_CUDA(cudaMemcpy2D(loglike, rows * sizeof(double), s.rec_ll, cap * sizeof(double), rows * sizeof(double), groups,
+                         cudaMemcpyDeviceToHost));
+  if (logprior)
+    CC_CUDA(cudaMemcpy2D(logprior, rows * sizeof(double), s.rec_lp, cap * sizeof(double), rows * sizeof(double), groups,
+                         cudaMemcpyDeviceToHost));
+  if (iteration) std::copy(r->rec_iter.begin(), r->rec_iter.end(), iteration);
+  return CC_OK;
+}
+
+extern "C" int cc_mcmc_device_draws(cc_mcmc* r, double** theta, double** loglike, double** logprior, int64_t* rows_cap) {
+  if (!r) return fail(CC_E_INVALID, "cc_mcmc_device_draws: null state");
+  if (theta) *theta = r->s.rec_theta;
+  if (loglike) *loglike = r->s.rec_ll;
+  if (logprior) *logprior = r->s.rec_lp;
+  if (rows_cap) *rows_cap = r->s.rows_cap;
+  return CC_OK;
+}
+
+extern "C" int cc_mcmc_diagnostics(cc_mcmc* r, double* beta, double* mc_accept, double* move_accept, double* bw) {
+  if (!r) return fail(CC_E_INVALID, "cc_mcmc_diagnostics: null state");
+  CC_CUDA(cudaSetDevice(r->m->device));
+  const McmcState& s = r->s;
+  CC_CUDA(cudaStreamSynchronize(r->m->stream));
+  const size_t P = (size_t)s.n_chains * s.rungs, d = (size_t)s.d;
+  if (beta) std::copy(r->beta.begin(), r->beta.end(), beta);
+  if (mc_accept && s.rungs > 1) {
+    const size_t n = (size_t)s.n_chains * (s.rungs - 1);
+    std::vector<unsigned> a(n), t(n);
+    CC_CUDA(cudaMemcpy(a.data(), s.swap_acc, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CC_CUDA(cudaMemcpy(t.data(), s.swap_try, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) mc_accept[i] = t[i] ? (double)a[i] / (double)t[i] : NAN;
+  }
+  if (move_accept) {
+    std::vector<unsigned> a(P * d);
+    CC_CUDA(cudaMemcpy(a.data(), s.move_acc, P * d * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < P * d; i++) move_accept[i] = (double)a[i];
+  }
+  if (bw) CC_CUDA(cudaMemcpy(bw, s.bw, P * d * sizeof(double), cudaMemcpyDeviceToHost));
+  return CC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ measurement
+extern "C" int cc_fp64_peak_probe(int device, int iters, double* tflops, double* ms_out) {
+  int ndev = cc_device_count();
+  if (ndev <= 0) return fail(CC_E_CUDA, "no CUDA device available");
+  if (device < 0 || device >= ndev) return fail(CC_E_INVALID, "device index out of range");
+  if (iters < 1) iters = 4096;
+  CC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CC_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* dummy = nullptr;
+  CC_CUDA(cudaMalloc((void**)&dummy, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CC_CUDA(cudaEventCreate(&e0));
+  CC_CUDA(cudaEventCreate(&e1));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CC_CUDA(cudaEventRecord(e0, 0));
+    fp64_probe_kernel<<<blocks, threads>>>(dummy, iters, 0.999999, 1e-7);
+    CC_CUDA(cudaEventRecord(e1, 0));
+    CC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dummy);
+  const double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+  if (tflops) *tflops = flops / ((double)best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return CC_OK;
+}

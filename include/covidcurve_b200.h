@@ -1,0 +1,208 @@
+/*
+ * covidcurve_b200.h - C ABI of the B200-native (sm_100a, FP64 CUDA) COVIDCurve hot path.
+ *
+ * Drop-in boundary.  In the reference the hot path is reached through drjacoby's user-function slot:
+ *
+ *     SEXP loglike (Rcpp::NumericVector params, int param_i, Rcpp::List data, Rcpp::List misc)   R/Agecpp2strings.R:389
+ *     SEXP logprior(Rcpp::NumericVector params, int param_i, Rcpp::List misc)                    R/Agecpp2strings.R:213
+ *     drjacoby::run_mcmc(data, df_params, misc, loglike, logprior, burnin, samples, chains,
+ *                        rungs, coupling_on, GTI_pow, beta_manual, ...)                          R/main.R:179-193
+ *
+ * and, for the static test twins, through
+ *     .Call("_COVIDCurve_natcubspline_loglike_binomial" | "..._logit", params, param_i, data, misc)
+ *                                                                     src/RcppExports.cpp:10-46, R/RcppExports.R:4-10
+ *
+ * This header is what an R .Call shim (covidcurve_b200/r/ccb200_shim.c), Python ctypes
+ * (covidcurve_b200/_lib.py) or any other FFI binds instead.  Plain pointers and sizes only; every function
+ * returns 0 on success or a negative CC_E_* code, with a message available from cc_last_error().
+ * Numerical failure is NOT an error: exactly like the reference (binomial.cpp:88-96,170-184,345-347 and
+ * Agecpp2strings.R:216) it is encoded in-band as the value -DBL_MAX/100.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device and fails with CC_E_CUDA otherwise.
+ */
+#ifndef COVIDCURVE_B200_H
+#define COVIDCURVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_ABI_VERSION 1
+
+/* compile-time capacity of one model (checked by cc_model_create) */
+#define CC_MAX_PARAMS 128
+#define CC_MAX_STRATA 32
+#define CC_MAX_KNOTS 16
+#define CC_MAX_SEROSURVEYS 16
+#define CC_MAX_DAYS 1024
+
+/* error codes */
+#define CC_OK 0
+#define CC_E_INVALID (-1) /* bad argument / descriptor */
+#define CC_E_CUDA (-2)    /* CUDA runtime error or no device */
+#define CC_E_NOMEM (-3)
+#define CC_E_STATE (-4)   /* call out of order (e.g. mcmc step before init) */
+
+/* memory space of caller-owned buffers */
+#define CC_MEM_HOST 0
+#define CC_MEM_DEVICE 1
+
+/* prior families of the generated logprior (R/Agecpp2strings.R:73-148) */
+#define CC_PRIOR_NONE 0
+#define CC_PRIOR_DUNIF 1 /* R::dunif(x, p1, p2, true) */
+#define CC_PRIOR_DNORM 2 /* R::dnorm(x, p1, p2, true) */
+#define CC_PRIOR_DBETA 3 /* R::dbeta(x, p1, p2, true) */
+
+/* The value the reference returns for an invalid proposal: -(DBL_MAX/100) */
+#define CC_OVERFLO_LOGLIKE (-1.797693134862315708e+306)
+
+/*
+ * Model descriptor = data_list + misc_list + df_params + the name->array mapping and prior literals that
+ * R/Agecpp2strings.R bakes into the generated C++ strings.  All pointers are HOST pointers, copied by
+ * cc_model_create (the caller may free them afterwards).
+ */
+typedef struct cc_model_desc {
+  int32_t abi_version; /* CC_ABI_VERSION */
+  /* sizes */
+  int32_t n_params;         /* d = nrow(df_params), R/main.R:172 */
+  int32_t n_strata;         /* A = length(misc$demog) */
+  int32_t n_knots;          /* K = misc$n_knots (incl. the fixed knot at day 1) */
+  int32_t days_obsd;        /* T = misc$days_obsd */
+  int32_t n_sero_obs;       /* S = misc$n_sero_obs */
+  int32_t max_seroday_obsd; /* M = misc$max_seroday_obsd (<= T) */
+  int32_t rcensor_day;      /* misc$rcensor_day (INT_MAX = no censoring) */
+  int32_t account_serorev;  /* misc$account_serorev */
+  int32_t binomial_likelihood; /* 1: natcubicspline_loglike_binomial.cpp, 0: ..._logit.cpp */
+  int32_t reparam_ifr, reparam_knots, reparam_infxn; /* run_IFRmodel_age(reparamIFR=, reparamKnots=, reparamInfxn=) */
+  /* misc / data */
+  const double* demog;                  /* [A] misc$demog (popN; truncated to int like the reference, binomial.cpp:10) */
+  const double* obs_deaths;             /* [T] data$obs_deaths, -1 = missing (truncated to int, binomial.cpp:204) */
+  const double* prop_strata_obs_deaths; /* [A] data$prop_strata_obs_deaths */
+  const double* sero_a;                 /* [S*A] data$obs_serologypos | data$obs_serologymu, survey-major */
+  const double* sero_b;                 /* [S*A] data$obs_serologyn   | data$obs_serologyse */
+  const int32_t* sero_survey_start;     /* [S] 1-based inclusive */
+  const int32_t* sero_survey_end;       /* [S] 1-based inclusive */
+  /* role map: row (0-based, df_params order) that feeds each model quantity (Agecpp2strings.R:261-368) */
+  int32_t idx_sens, idx_spec, idx_sero_con_rate;
+  int32_t idx_sero_rev_shape, idx_sero_rev_scale; /* -1 when !account_serorev */
+  int32_t idx_mod, idx_sod;
+  const int32_t* idx_knots; /* [K-1] rows of node_x[1..K-1]; scaled by params[idx_rel_knot] when reparam_knots and row != idx_rel_knot */
+  const int32_t* idx_infxn; /* [K]   rows of node_y[0..K-1]; same rule with idx_rel_infxn */
+  const int32_t* idx_ifr;   /* [A]   rows of ma[0..A-1];     same rule with idx_max_ma */
+  const int32_t* idx_noise; /* [A]   rows of ne[0..A-1] (ignored when A == 1) */
+  int32_t idx_rel_knot, idx_rel_infxn, idx_max_ma; /* -1 when the matching reparam flag is 0 */
+  /* df_params bounds (drjacoby transform: all four finite/infinite combinations are supported) */
+  const double* pmin; /* [d] may be -INFINITY */
+  const double* pmax; /* [d] may be +INFINITY */
+  /* prior table (literals of the generated logprior) */
+  const int32_t* prior_family; /* [d] CC_PRIOR_* */
+  const double* prior_p1;      /* [d] paramdf$dsc1 */
+  const double* prior_p2;      /* [d] paramdf$dsc2 */
+  int32_t jac_rows[3];         /* rows of maxMa, relKnot, relInfxn or -1 */
+  double jac_counts[3];        /* number of scalars multiplied by each (A-1, K-2, K-1) */
+} cc_model_desc;
+
+typedef struct cc_model cc_model; /* opaque: owns the device copy of the descriptor and all scratch */
+
+const char* cc_last_error(void);
+int cc_abi_version(void);
+int cc_device_count(void);
+
+/* Create / destroy a model bound to CUDA device `device`. */
+int cc_model_create(const cc_model_desc* desc, int device, cc_model** out);
+void cc_model_destroy(cc_model* m);
+
+/*
+ * Batched drop-in for loglike(params, param_i, data, misc) (R/Agecpp2strings.R:389; param_i is ignored by the
+ * reference, binomial.cpp:7, so it is not part of the batch call).
+ *   theta : structure-of-arrays [d][ld], element (p, i) at theta[p*ld + i], i < n  (n contiguous -> coalesced)
+ *   out   : [n] log-likelihoods
+ *   mem   : CC_MEM_HOST (library stages through pinned memory) or CC_MEM_DEVICE (pointers on `device`)
+ *   stream: cudaStream_t as void* (NULL = the library's own stream); the call is synchronous for CC_MEM_HOST and
+ *           stream-ordered (asynchronous) for CC_MEM_DEVICE.
+ */
+int cc_loglike_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* out, int mem, void* stream);
+/* Batched drop-in for logprior(params, param_i, misc) (R/Agecpp2strings.R:213). Same conventions. */
+int cc_logprior_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* out, int mem, void* stream);
+
+/* Scalar drop-ins (batch of one, host pointers) for the .Call twins _COVIDCurve_natcubspline_loglike_* . */
+int cc_loglike(cc_model* m, const double* params, int param_i, double* out);
+int cc_logprior(cc_model* m, const double* params, int param_i, double* out);
+
+/*
+ * Intermediates of one evaluation, for the post-processing re-entry points (R/summarize_plot.R:276-884):
+ * any output pointer may be NULL.  Host pointers.  Batched over n parameter vectors (SoA like above).
+ *   infxn    [n][T]   exp(spline) incidence                 (draw_posterior_infxn_cubic_splines, per stratum = ne[a]*infxn)
+ *   ne       [n][A]   normalised attack-rate weights
+ *   auc      [n][T]   death-delay convolution (expected deaths per day before IFR weighting)
+ *   sero_full[n][T]   sum_i infxn[i]*hazard[j-i] over ALL days_obsd (draw_posterior_sero_curves, x ne[a])
+ */
+int cc_curves_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* infxn, double* ne, double* auc,
+                    double* sero_full);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GPU-resident Metropolis-coupled MCMC replacing drjacoby::run_mcmc (call site R/main.R:179-193).
+ * One particle per (chain, rung); single-site Metropolis-Hastings sweep over the d parameters with
+ * Robbins-Monro proposal adaptation, then one pass of adjacent-rung swaps; device RNG (Philox4x32-10 keyed
+ * by seed, global chain id, rung, iteration, parameter).  Chains are independent: shard them over GPUs by
+ * giving each process a [chain_offset, chain_offset + n_chains) slice - results do not depend on the split.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct cc_mcmc_opts {
+  int32_t burnin;        /* drjacoby burnin  (iterations 1..burnin; iteration 1 is the initial state) */
+  int32_t samples;       /* drjacoby samples */
+  int32_t rungs;
+  int32_t n_chains;      /* chains simulated by THIS model handle */
+  int32_t chain_offset;  /* global id of the first local chain (RNG keying) */
+  int32_t coupling_on;
+  double GTI_pow;
+  const double* beta_manual; /* NULL or [rungs] */
+  uint64_t seed;
+  int32_t cold_rung_last; /* 1 (default, drjacoby 1.2.0): beta ascending, rung index R-1 is the cold chain */
+  int32_t record_rungs;   /* 0: record only the cold rung, 1: record every rung (drjacoby records all) */
+  int32_t thin;           /* record every thin-th iteration (0/1 = all) */
+  const double* init;     /* NULL (use `init_default` of every chain) or [n_chains][d] */
+  const double* init_default; /* [d] df_params$init */
+  int32_t bw_per_particle;      /* 0 (default): proposal bandwidths belong to the rung (temperature); 1: they travel with
+                                   the particle through swaps (drjacoby 1.2.0 swaps beta between particles) */
+  int32_t no_adapt_in_sampling; /* 0 (default): Robbins-Monro keeps adapting during sampling (drjacoby 1.2.0); 1: burn-in only */
+} cc_mcmc_opts;
+
+typedef struct cc_mcmc cc_mcmc; /* opaque run state, device resident */
+
+int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* opts, cc_mcmc** out);
+/* advance `n_iter` iterations (sweep + swap each); records draws on the device */
+int cc_mcmc_advance(cc_mcmc* s, int32_t n_iter);
+/* iterations done so far (1 after create: the initial state is iteration 1) */
+int64_t cc_mcmc_iterations(const cc_mcmc* s);
+/* number of recorded rows per (chain, recorded rung) so far */
+int64_t cc_mcmc_rows(const cc_mcmc* s);
+/*
+ * Copy recorded draws to host buffers: theta [n_chains][n_rec_rungs][rows][d], loglike/logprior
+ * [n_chains][n_rec_rungs][rows], iteration [rows] (1-based).  Any pointer may be NULL.
+ */
+int cc_mcmc_fetch(cc_mcmc* s, double* theta, double* loglike, double* logprior, int32_t* iteration);
+/* device pointers of the recorded draws (for NCCL allgather / device-side summaries):
+   theta [n_chains][n_rec_rungs][rows_cap][d], loglike/logprior [n_chains][n_rec_rungs][rows_cap]; only the first
+   cc_mcmc_rows() rows of each group are valid; *rows_cap = (burnin + samples) / thin */
+int cc_mcmc_device_draws(cc_mcmc* s, double** theta, double** loglike, double** logprior, int64_t* rows_cap);
+/* diagnostics: beta [rungs]; mc_accept [n_chains][rungs-1] swap acceptance rate over the sampling phase;
+   move_accept [n_chains][rungs][d] single-site acceptance counts; bw [n_chains][rungs][d] proposal bandwidths */
+int cc_mcmc_diagnostics(cc_mcmc* s, double* beta, double* mc_accept, double* move_accept, double* bw);
+/* number of likelihood evaluations performed so far (full-evaluation equivalents = proposals) */
+int64_t cc_mcmc_loglike_evals(const cc_mcmc* s);
+void cc_mcmc_destroy(cc_mcmc* s);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): live FP64 FMA peak of the device, and kernel time of the last batch call.
+ * --------------------------------------------------------------------------------------------------------- */
+/* Register-resident DFMA chain micro-benchmark; returns achieved TFLOP/s (FMA = 2 flops) in *tflops. */
+int cc_fp64_peak_probe(int device, int iters, double* tflops, double* ms);
+/* CUDA-event duration (ms) of the most recent cc_loglike_batch kernel on this model, and #kernels it launched. */
+int cc_last_kernel_ms(cc_model* m, double* ms, int32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVIDCURVE_B200_H */
