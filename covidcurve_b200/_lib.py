@@ -75,6 +75,7 @@ SYMBOLS = {
     "cc_mcmc_diagnostics": (C.c_int, [_vp, c_dp, c_dp, c_dp, c_dp]),
     "cc_mcmc_loglike_evals": (C.c_int64, [_vp]),
     "cc_mcmc_destroy": (None, [_vp]),
+    "cc_nmath_batch": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_int64, c_dp]),
     "cc_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
     "cc_last_kernel_ms": (C.c_int, [_vp, c_dp, C.POINTER(C.c_int32)]),
 }
@@ -292,6 +293,18 @@ class Mcmc:
         bw = np.empty((P, self.d))
         check(self.L.cc_mcmc_diagnostics(self.h, _dp(beta), _dp(mc), _dp(mv), _dp(bw)))
         return dict(beta=beta, mc_accept=mc, move_accept=mv, bw=bw.reshape(self.chains, self.rungs, self.d))
+
+
+FN = dict(pgamma=1, dpois=2, dbinom=3, dnorm=4, dbeta=5, dunif=6, pweibull=7, stirlerr=8, bd0=9)
+
+
+def nmath(fn: str, a, b=0.0, c=0.0, device: int = 0):
+    """Element-wise device evaluation of one of the R nmath routines on the path (test hook)."""
+    a, b, c = np.broadcast_arrays(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), np.asarray(c, dtype=np.float64))
+    a, b, c = (np.ascontiguousarray(v).ravel() for v in (a, b, c))
+    out = np.empty(a.size)
+    check(load().cc_nmath_batch(device, FN[fn], _dp(a), _dp(b), _dp(c), a.size, _dp(out)))
+    return out
 
 
 def fp64_peak_probe(device: int = 0, iters: int = 4096):

@@ -47,12 +47,12 @@ struct EvalSmem {
   double* ch;     // [M+1]  prefix sums of haz
   double* tmp1;   // [M]    serorev: seroconversion density
   double* tmp2;   // [M]    serorev: 1 - weibull cdf
-  double* red;    // [64]   reduction scratch
+  double* red;    // [128]  reduction scratch (block_sum<4> needs 4 x 32)
   Scalars* sc;
 };
 
 __host__ __device__ inline size_t eval_smem_bytes(int d, int T, int M) {
-  size_t n = (size_t)d + (T + 1) + 3 * (size_t)T + 4 * (size_t)M + 1 + 64 + 8;
+  size_t n = (size_t)d + (T + 1) + 3 * (size_t)T + 4 * (size_t)M + 1 + 128 + 8;
   return n * sizeof(double) + sizeof(Scalars) + 16;
 }
 
@@ -68,7 +68,7 @@ __device__ inline EvalSmem carve_smem(unsigned char* base, int d, int T, int M) 
   s.ch = q; q += M + 1;
   s.tmp1 = q; q += M;
   s.tmp2 = q; q += M;
-  s.red = q; q += 64;
+  s.red = q; q += 128;
   uintptr_t a = (reinterpret_cast<uintptr_t>(q) + 15) & ~uintptr_t(15);
   s.sc = reinterpret_cast<Scalars*>(a);
   return s;

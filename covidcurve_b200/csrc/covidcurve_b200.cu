@@ -818,6 +818,54 @@ extern "C" int cc_mcmc_diagnostics(cc_mcmc* r, double* beta, double* mc_accept, 
   return CC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ nmath test hook
+__global__ void nmath_kernel(int fn, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                             long long n, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = a[i], y = b[i], z = c[i];
+  double r;
+  switch (fn) {
+    case CC_FN_PGAMMA: {  // pgamma(x, shape = y, scale = z), lower tail
+      if (isnan(x) || isnan(y) || isnan(z)) r = x + y + z;
+      else if (y < 0 || z <= 0) r = d_nan();
+      else r = pgamma_lower(gamma_shape(y), x / z);
+      break;
+    }
+    case CC_FN_DPOIS: r = dpois_log_int(x, y); break;
+    case CC_FN_DBINOM: r = dbinom_log(x, y, z); break;
+    case CC_FN_DNORM: r = dnorm_log(x, y, z); break;
+    case CC_FN_DBETA: r = dbeta_log(x, y, z); break;
+    case CC_FN_DUNIF: r = dunif_log(x, y, z); break;
+    case CC_FN_PWEIBULL: r = pweibull_lower(x, y, z); break;
+    case CC_FN_STIRLERR: r = stirlerr(x); break;
+    case CC_FN_BD0: r = bd0(x, y); break;
+    default: r = d_nan();
+  }
+  out[i] = r;
+}
+
+extern "C" int cc_nmath_batch(int device, int fn, const double* a, const double* b, const double* c, int64_t n, double* out) {
+  if (!a || !b || !c || !out || n < 0) return fail(CC_E_INVALID, "cc_nmath_batch: bad argument");
+  if (fn < CC_FN_PGAMMA || fn > CC_FN_BD0) return fail(CC_E_INVALID, "cc_nmath_batch: unknown function id");
+  if (cc_device_count() <= 0) return fail(CC_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (n == 0) return CC_OK;
+  CC_CUDA(cudaSetDevice(device));
+  double* d = nullptr;
+  CC_CUDA(cudaMalloc((void**)&d, (size_t)4 * n * sizeof(double)));
+  cudaError_t e = cudaMemcpy(d, a, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + n, b, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + 2 * n, c, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    nmath_kernel<<<(unsigned)((n + 127) / 128), 128>>>(fn, d, d + n, d + 2 * n, n, d + 3 * n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(CC_E_CUDA, std::string("cc_nmath_batch: ") + cudaGetErrorString(e));
+  return CC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ measurement
 extern "C" int cc_fp64_peak_probe(int device, int iters, double* tflops, double* ms_out) {
   int ndev = cc_device_count();

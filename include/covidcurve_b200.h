@@ -195,6 +195,26 @@ int64_t cc_mcmc_loglike_evals(const cc_mcmc* s);
 void cc_mcmc_destroy(cc_mcmc* s);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Device versions of the R nmath routines the path calls (binomial.cpp:79,216,248,269,337; logit.cpp:337;
+ * Agecpp2strings.R:73-148), exposed element-wise so that they can be checked against R's values in isolation.
+ * Host pointers, n elements each; out[i] = fn(a[i], b[i], c[i]) with log = TRUE for the densities:
+ *   CC_FN_PGAMMA   pgamma(x=a, shape=b, scale=c, lower, non-log)     CC_FN_DPOIS  dpois(x=a, lambda=b)
+ *   CC_FN_DBINOM   dbinom(x=a, n=b, p=c)   CC_FN_DNORM dnorm(a, mu=b, sd=c)   CC_FN_DBETA dbeta(a, b, c)
+ *   CC_FN_DUNIF    dunif(a, b, c)          CC_FN_PWEIBULL pweibull(a, shape=b, scale=c)
+ *   CC_FN_STIRLERR stirlerr(a)             CC_FN_BD0   bd0(a, b)
+ * --------------------------------------------------------------------------------------------------------- */
+#define CC_FN_PGAMMA 1
+#define CC_FN_DPOIS 2
+#define CC_FN_DBINOM 3
+#define CC_FN_DNORM 4
+#define CC_FN_DBETA 5
+#define CC_FN_DUNIF 6
+#define CC_FN_PWEIBULL 7
+#define CC_FN_STIRLERR 8
+#define CC_FN_BD0 9
+int cc_nmath_batch(int device, int fn, const double* a, const double* b, const double* c, int64_t n, double* out);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): live FP64 FMA peak of the device, and kernel time of the last batch call.
  * --------------------------------------------------------------------------------------------------------- */
 /* Register-resident DFMA chain micro-benchmark; returns achieved TFLOP/s (FMA = 2 flops) in *tflops. */

@@ -19,7 +19,23 @@
 
 #include "nmath_port.h"
 
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+#endif
+
 namespace {
+
+/* R evaluates the likelihood with IEEE gradual underflow.  A host process that has loaded a library built with
+   -ffast-math (several Python extension modules are) runs with MXCSR flush-to-zero / denormals-are-zero set, and
+   threads inherit it; tiny gamma-cdf values would then flush to 0 and turn finite log-likelihoods into the in-band
+   failure value.  Every oracle entry point therefore clears FTZ/DAZ for its own duration. */
+struct IeeeGuard {
+#if defined(__x86_64__) || defined(__i386__)
+  unsigned saved;
+  IeeeGuard() : saved(_mm_getcsr()) { _mm_setcsr(saved & ~0x8040u); }
+  ~IeeeGuard() { _mm_setcsr(saved); }
+#endif
+};
 
 /* Rcpp's params["name"]: linear scan over the names attribute (R/Agecpp2strings.R:261 etc.) */
 double by_name(const cco_desc* m, const double* params, const char* name) {
@@ -63,6 +79,7 @@ void fill_role(const cco_desc* m, const double* params, const char* const* role,
 }  // namespace
 
 extern "C" double cco_loglike(const cco_desc* m, const double* params, int /*param_i*/, cco_trace* tr) {
+  IeeeGuard ieee_guard;
   /* ---- generated prologue, R/Agecpp2strings.R:255-368 ---- */
   std::vector<int> demog(m->A);
   for (int a = 0; a < m->A; a++) demog[a] = (int)m->demog[a];
@@ -306,6 +323,7 @@ extern "C" double cco_loglike(const cco_desc* m, const double* params, int /*par
    IFR dunif, knot dunif, infxn dunif, sero (con_rate dnorm, sens dbeta, spec dbeta[, rev shape, rev scale dnorm]),
    noise dnorm, mod dnorm, sod dbeta, then the Jacobian terms. */
 extern "C" double cco_logprior(const cco_desc* m, const double* params, int /*param_i*/) {
+  IeeeGuard ieee_guard;
   const int A = m->A, K = m->n_knots;
   auto idx = [&](const char* nm) {
     for (int i = 0; i < m->d; i++)

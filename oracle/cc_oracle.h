@@ -92,12 +92,18 @@ typedef struct cco_mcmc_opts {
   unsigned long long seed;
   int nthreads;              /* chains are farmed over threads like drjacoby's cluster= */
   int cold_rung_last;        /* 1: beta ascending, rung{R} is cold (drjacoby 1.2.0); 0: rung1 cold */
+  int init_per_chain;        /* 0: init is [d] shared by all chains; 1: init is [chains][d] */
+  int chain_offset;          /* global id of chain 0 (RNG keying) */
 } cco_mcmc_opts;
 
 /* out_theta: [chains][rungs][burnin+samples][d]; out_ll/out_lp: [chains][rungs][burnin+samples];
    out_accept: [chains][rungs-1] coupling acceptance counts over sampling (may be NULL); beta_out [rungs] */
 int cco_mcmc(const cco_desc* m, const double* init, const cco_mcmc_opts* o, double* out_theta, double* out_ll,
              double* out_lp, double* out_accept, double* beta_out);
+/* known-answer access to the restated Philox4x32-10 and to the (normal, uniform) draw of one proposal */
+int cco_philox_kat(const unsigned ctr[4], const unsigned key[2], unsigned out[4]);
+void cco_draw(unsigned long long seed, unsigned stream, unsigned chain, unsigned id, unsigned iteration, unsigned param,
+              double* z, double* u);
 
 #ifdef __cplusplus
 }

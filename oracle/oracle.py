@@ -41,7 +41,8 @@ class _Trace(C.Structure):
 class _McmcOpts(C.Structure):
     _fields_ = [("burnin", C.c_int), ("samples", C.c_int), ("rungs", C.c_int), ("chains", C.c_int),
                 ("coupling_on", C.c_int), ("GTI_pow", C.c_double), ("beta_manual", c_dp),
-                ("seed", C.c_ulonglong), ("nthreads", C.c_int), ("cold_rung_last", C.c_int)]
+                ("seed", C.c_ulonglong), ("nthreads", C.c_int), ("cold_rung_last", C.c_int),
+                ("init_per_chain", C.c_int), ("chain_offset", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -81,6 +82,10 @@ def lib():
             getattr(L, name).argtypes = [C.POINTER(_Desc), c_dp, C.c_long, c_dp, C.c_int]
         L.cco_mcmc.restype = C.c_int
         L.cco_mcmc.argtypes = [C.POINTER(_Desc), c_dp, C.POINTER(_McmcOpts), c_dp, c_dp, c_dp, c_dp, c_dp]
+        L.cco_philox_kat.restype = C.c_int
+        L.cco_philox_kat.argtypes = [C.POINTER(C.c_uint)] * 3
+        L.cco_draw.restype = None
+        L.cco_draw.argtypes = [C.c_ulonglong] + [C.c_uint] * 5 + [c_dp, c_dp]
         _lib = L
     return _lib
 
@@ -152,9 +157,11 @@ class Oracle:
         return bufs
 
     def mcmc(self, burnin, samples, rungs=1, chains=1, coupling_on=True, GTI_pow=1.0, beta_manual=None, seed=1,
-             nthreads=1, cold_rung_last=True, init=None):
+             nthreads=1, cold_rung_last=True, init=None, chain_offset=0):
         s = self.spec
         init = np.ascontiguousarray(s.pinit if init is None else init, dtype=np.float64)
+        per_chain = init.ndim == 2
+        assert init.shape == ((chains, s.d) if per_chain else (s.d,))
         n_it = burnin + samples
         theta = np.zeros((chains, rungs, n_it, s.d))
         ll = np.zeros((chains, rungs, n_it))
@@ -164,7 +171,7 @@ class Oracle:
         bm = None if beta_manual is None else np.ascontiguousarray(beta_manual, dtype=np.float64)
         o = _McmcOpts(burnin=burnin, samples=samples, rungs=rungs, chains=chains, coupling_on=int(coupling_on),
                       GTI_pow=GTI_pow, beta_manual=_dp(bm) if bm is not None else None, seed=seed, nthreads=nthreads,
-                      cold_rung_last=int(cold_rung_last))
+                      cold_rung_last=int(cold_rung_last), init_per_chain=int(per_chain), chain_offset=chain_offset)
         rc = self.L.cco_mcmc(C.byref(self.desc), _dp(init), C.byref(o), _dp(theta), _dp(ll), _dp(lp), _dp(acc), _dp(beta))
         if rc != 0:
             raise RuntimeError("oracle mcmc failed rc=%d" % rc)
