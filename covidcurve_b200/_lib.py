@@ -77,6 +77,7 @@ SYMBOLS = {
     "cc_mcmc_destroy": (None, [_vp]),
     "cc_nmath_batch": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_int64, c_dp]),
     "cc_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
+    "cc_dmma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "cc_last_kernel_ms": (C.c_int, [_vp, c_dp, C.POINTER(C.c_int32)]),
 }
 
@@ -312,3 +313,10 @@ def fp64_peak_probe(device: int = 0, iters: int = 4096):
     t, ms = C.c_double(), C.c_double()
     check(load().cc_fp64_peak_probe(device, iters, C.byref(t), C.byref(ms)))
     return t.value, ms.value
+
+
+def dmma_probe(device: int = 0, iters: int = 4096, fma_per_mma: int = 0):
+    """(mma TFLOP/s, concurrent fma TFLOP/s, ms) of the FP64 tensor-core probe."""
+    a, b, ms = C.c_double(), C.c_double(), C.c_double()
+    check(load().cc_dmma_probe(device, iters, fma_per_mma, C.byref(a), C.byref(b), C.byref(ms)))
+    return a.value, b.value, ms.value

@@ -267,6 +267,34 @@ __global__ void fp64_probe_kernel(double* out, int iters, double a, double b) {
   if (sum == 123.456) out[0] = sum;  // keep the chains alive without a store in the common case
 }
 
+// ---- FP64 tensor-core (DMMA m8n8k4) probe, optionally interleaved with independent DFMA chains, to learn whether
+// the two share a pipe on this part (decides where the Toeplitz contraction should run).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int NFMA>
+__global__ void dmma_probe_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int u = 0; u < 8; u++) c[u][0] = c[u][1] = threadIdx.x * 1e-9 + u;
+  double x[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) x[u] = threadIdx.x * 1e-9 + u;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      dmma884(c[u][0], c[u][1], a, b);
+#pragma unroll
+      for (int f = 0; f < NFMA; f++) x[(u + f) & 7] = fma(x[(u + f) & 7], a, b);
+    }
+  }
+  double sum = 0;
+#pragma unroll
+  for (int u = 0; u < 8; u++) sum += c[u][0] + c[u][1] + x[u];
+  if (sum == 123.456) out[0] = sum;
+}
+
 // ------------------------------------------------------------------------------------------------ model
 static double host_stirlerr(double n) {
   const double S0 = 0.083333333333333333333, S1 = 0.00277777777777777777778, S2 = 0.00079365079365079365079365,
@@ -882,7 +910,7 @@ extern "C" int cc_fp64_peak_probe(int device, int iters, double* tflops, double*
   CC_CUDA(cudaEventCreate(&e1));
   const int threads = 256, blocks = prop.multiProcessorCount * 8;
   float best = 1e30f;
-  for (int rep = 0; rep < 5; rep++) {
+  for (int rep = 0; rep < 8; rep++) {
     CC_CUDA(cudaEventRecord(e0, 0));
     fp64_probe_kernel<<<blocks, threads>>>(dummy, iters, 0.999999, 1e-7);
     CC_CUDA(cudaEventRecord(e1, 0));
@@ -896,6 +924,49 @@ extern "C" int cc_fp64_peak_probe(int device, int iters, double* tflops, double*
   cudaFree(dummy);
   const double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
   if (tflops) *tflops = flops / ((double)best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return CC_OK;
+}
+
+extern "C" int cc_dmma_probe(int device, int iters, int fma_per_mma, double* mma_tflops, double* fma_tflops, double* ms_out) {
+  int ndev = cc_device_count();
+  if (ndev <= 0) return fail(CC_E_CUDA, "no CUDA device available");
+  if (device < 0 || device >= ndev) return fail(CC_E_INVALID, "device index out of range");
+  if (iters < 1) iters = 4096;
+  CC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CC_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* dummy = nullptr;
+  CC_CUDA(cudaMalloc((void**)&dummy, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CC_CUDA(cudaEventCreate(&e0));
+  CC_CUDA(cudaEventCreate(&e1));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CC_CUDA(cudaEventRecord(e0, 0));
+    switch (fma_per_mma) {
+      case 0: dmma_probe_kernel<0><<<blocks, threads>>>(dummy, iters, 0.999999, 1e-7); break;
+      case 1: dmma_probe_kernel<1><<<blocks, threads>>>(dummy, iters, 0.999999, 1e-7); break;
+      case 2: dmma_probe_kernel<2><<<blocks, threads>>>(dummy, iters, 0.999999, 1e-7); break;
+      case 4: dmma_probe_kernel<4><<<blocks, threads>>>(dummy, iters, 0.999999, 1e-7); break;
+      case 8: dmma_probe_kernel<8><<<blocks, threads>>>(dummy, iters, 0.999999, 1e-7); break;
+      default: cudaFree(dummy); return fail(CC_E_INVALID, "fma_per_mma must be 0, 1, 2, 4 or 8");
+    }
+    CC_CUDA(cudaEventRecord(e1, 0));
+    CC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dummy);
+  const double warps = (double)threads / 32 * blocks;
+  const double mma_flops = 2.0 * 256.0 * 8.0 * (double)iters * warps;                       // 8x8x4 FMAs per warp-level mma
+  const double fma_flops = 2.0 * 8.0 * fma_per_mma * (double)iters * (double)threads * blocks;
+  if (mma_tflops) *mma_tflops = mma_flops / ((double)best * 1e-3) / 1e12;
+  if (fma_tflops) *fma_tflops = fma_flops / ((double)best * 1e-3) / 1e12;
   if (ms_out) *ms_out = best;
   return CC_OK;
 }

@@ -219,6 +219,9 @@ int cc_nmath_batch(int device, int fn, const double* a, const double* b, const d
  * --------------------------------------------------------------------------------------------------------- */
 /* Register-resident DFMA chain micro-benchmark; returns achieved TFLOP/s (FMA = 2 flops) in *tflops. */
 int cc_fp64_peak_probe(int device, int iters, double* tflops, double* ms);
+/* FP64 tensor-core (mma.sync m8n8k4 f64) micro-benchmark with `fma_per_mma` (0, 1, 2, 4, 8) independent DFMAs issued per
+   warp-level MMA: tells whether DMMA and DFMA share a pipe on this device (death-delay convolution). */
+int cc_dmma_probe(int device, int iters, int fma_per_mma, double* mma_tflops, double* fma_tflops, double* ms);
 /* CUDA-event duration (ms) of the most recent cc_loglike_batch kernel on this model, and #kernels it launched. */
 int cc_last_kernel_ms(cc_model* m, double* ms, int32_t* launches);
 
