@@ -1,0 +1,583 @@
+// cc_eval_tile.cuh - tile-phased evaluation: one warp owns a tile of E <= 32 parameter vectors and alternates between
+//   phase 1  (one LANE per vector)   everything that is scalar per vector: role map, attack-rate weights, knot check, spline
+//                                    coefficients, gamma-table constants (lgamma, logs, continued fraction of the tail), sero
+//                                    constants  -> a record per vector in an L2-resident scratch (structure-of-arrays per tile)
+//   phase 2  (the WARP per vector)   everything that is per day: delay-kernel masses, spline + exp, the two Toeplitz products on
+//                                    the FP64 tensor cores, the Poisson term, the survey-window sums
+//   phase 3  (one LANE per vector)   everything that is per stratum / survey: chained binomial, serology term, total + clamp.
+// Serial scalar code therefore runs 32 vectors wide instead of on one lane of a warp, every transcendental call site exists
+// once (the instruction footprint of the per-day loop is a few thousand instructions), and global loads/stores of theta/out
+// are perfectly coalesced (lane <-> consecutive vector).  For small batches (the Metropolis step) the tile is narrowed to
+// E = 1, 2, 4 ... vectors so that all warps of the GPU stay busy; phases 1 and 3 then run E lanes wide.
+//
+// Stage map and reference line numbers: see cc_eval_warp.cuh / SURVEY.md 3.2.
+#pragma once
+#include "cc_eval_warp.cuh"
+
+namespace ccdev {
+
+// ---- record layout (doubles); phase-2 fields first
+struct RecLayout {
+  int flags, gam, sero, snm, ne, spl, cday, n2;  // [0, n2) is what phase 2 loads
+  int nm, sens, spec, o_status, o_l1, o_texpd, o_sunc, o_base, F;
+};
+__host__ __device__ inline RecLayout rec_layout(int K, int A, int S) {
+  RecLayout L;
+  L.flags = 0;            // 1 = knots ordered
+  L.gam = 1;              // alph, scale, h, lgam_a, lsc, km, nser, QT, fast
+  L.sero = 10;            // rate, g1, g32, fac | rate, shape, lws, badw
+  L.snm = 14;
+  L.ne = 15;              // [A]
+  L.spl = L.ne + A;       // per interval j < K-1: x_j, y_j, sp1_j, sp2_j, sp3_j
+  L.cday = L.spl + 5 * (K - 1);  // cday[1..K-2]
+  L.n2 = L.cday + (K - 2);
+  L.nm = L.n2;            // [A]
+  L.sens = L.nm + A;
+  L.spec = L.sens + 1;
+  L.o_status = L.spec + 1;  // 0 ok, 1 population check failed
+  L.o_l1 = L.o_status + 1;
+  L.o_texpd = L.o_l1 + 1;
+  L.o_sunc = L.o_texpd + 1;
+  L.o_base = L.o_sunc + 1;  // [S]
+  L.F = L.o_base + S;
+  return L;
+}
+
+struct TileSmem {
+  double* rec;  // [n2 rounded] record of the vector being processed
+  double* xs;   // padded series
+  double* gs;   // kernel / later the convolution output in day order
+  double* sk;   // CH prefix sums
+  double* ctab; // [32]
+};
+__host__ __device__ inline size_t tile_smem_doubles(int K, int A, int S, int NT) {
+  const RecLayout L = rec_layout(K, A, S);
+  return (size_t)((L.n2 + 3) & ~3) + 12 * (8 * NT + 7) + (64 * NT + 16) + (64 * NT + 4) + 32;
+}
+__device__ inline TileSmem carve_tile(double* q, const RecLayout& L, int NT) {
+  TileSmem w;
+  w.rec = q; q += (L.n2 + 3) & ~3;
+  w.xs = q; q += 12 * (8 * NT + 7);
+  w.gs = q; q += 64 * NT + 16;
+  w.sk = q; q += 64 * NT + 4;
+  w.ctab = q;
+  return w;
+}
+__device__ inline void tile_smem_init(const TileSmem& w) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < kXsLead; i += 32) w.xs[i] = 0.0;
+  if (lane < 7) w.gs[lane] = 0.0;
+  __syncwarp();
+}
+
+// single out-of-line copies of the heavy scalar routines (instruction footprint)
+__device__ __noinline__ double dbinom_log_shared(double x, double n, double p) { return dbinom_log(x, n, p); }
+__device__ __forceinline__ double lgamma_shared(double x) { return lgamma(x); }
+
+// ------------------------------------------------------------------------------------------------ phase 1
+// `par(i)` returns parameter i of this lane's vector.  scr = tile scratch, field f of lane e at scr[f*32 + e].
+template <int NT, typename Par>
+__device__ inline void tile_phase1(const KModel& m, const RecLayout& L, double* __restrict__ scr, int e, Par par) {
+  const int K = m.K, A = m.A, T = m.T;
+  auto put = [&](int f, double v) { scr[f * 32 + e] = v; };
+  // ---- role map with the re-parameterisation lift (Agecpp2strings.R:277-355)
+  double nx[kMaxK], ny[kMaxK];
+  nx[0] = 1.0;
+  for (int i = 0; i < K - 1; i++) {
+    const int r = m.idx_knots[i];
+    double v = par(r);
+    if (m.reparam_knots && r != m.idx_rel_knot) v = v * par(m.idx_rel_knot);
+    nx[i + 1] = v;
+  }
+  for (int i = 0; i < K; i++) {
+    const int r = m.idx_infxn[i];
+    double v = par(r);
+    if (m.reparam_infxn && r != m.idx_rel_infxn) v = v * par(m.idx_rel_infxn);
+    ny[i] = v;
+  }
+  // ---- attack-rate weights (binomial.cpp:60-73) and ne*ma
+  double snm = 0.0;
+  {
+    double nedom = 0.0;
+    if (A > 1)
+      for (int a = 0; a < A; a++) nedom += par(m.idx_noise[a]) * (double)m.demog[a];
+    for (int a = 0; a < A; a++) {
+      const int r = m.idx_ifr[a];
+      double ma = par(r);
+      if (m.reparam_ifr && r != m.idx_max_ma) ma = ma * par(m.idx_max_ma);
+      const double ne = (A > 1) ? (par(m.idx_noise[a]) * (double)m.demog[a]) / nedom : (m.binomial ? 1.0 : 0.0);
+      put(L.ne + a, ne);
+      put(L.nm + a, ne * ma);
+      snm += ne * ma;
+    }
+  }
+  put(L.snm, snm);
+  put(L.sens, par(m.idx_sens));
+  put(L.spec, par(m.idx_spec));
+  // ---- knot order (binomial.cpp:88-96)
+  bool ok = true;
+  for (int i = 1; i < K; i++) ok = ok && (nx[i] > nx[i - 1]);
+  put(L.flags, ok ? 1.0 : 0.0);
+  if (!ok) return;
+  // ---- natural cubic spline, tridiagonal sweep (binomial.cpp:102-139)
+  {
+    double z[kMaxK], kk[kMaxK], rden[kMaxK];
+    for (int i = 0; i < K - 1; i++) rden[i] = 1.0 / (nx[i + 1] - nx[i]);
+    z[0] = 0.0;
+    kk[0] = 0.0;
+    for (int i = 1; i < K - 1; i++) {
+      const double mm = 3.0 * rden[i] * (ny[i + 1] - ny[i]) - 3.0 * rden[i - 1] * (ny[i] - ny[i - 1]);
+      const double den_im1 = nx[i] - nx[i - 1];
+      const double rg = 1.0 / (2.0 * (nx[i + 1] - nx[i - 1]) - den_im1 * kk[i - 1]);
+      kk[i] = (nx[i + 1] - nx[i]) * rg;
+      z[i] = (mm - den_im1 * z[i - 1]) * rg;
+    }
+    double sp2n = 0.0;
+    for (int i = K - 2; i >= 0; i--) {
+      const double den = nx[i + 1] - nx[i];
+      const double sp2i = z[i] - kk[i] * sp2n;
+      const int o = L.spl + 5 * i;
+      put(o, nx[i]);
+      put(o + 1, ny[i]);
+      put(o + 2, (ny[i + 1] - ny[i]) * rden[i] - (den * (sp2n + 2.0 * sp2i)) * (1.0 / 3.0));
+      put(o + 3, sp2i);
+      put(o + 4, (sp2n - sp2i) * (1.0 / 3.0) * rden[i]);
+      sp2n = sp2i;
+    }
+    // interval-lag rule in closed form (binomial.cpp:153-159)
+    double c = 0.0;
+    for (int mI = 1; mI <= K - 2; mI++) {
+      c = fmax(c + 1.0, ceil(nx[mI]) - 1.0);
+      put(L.cday + mI - 1, c);
+    }
+  }
+  // ---- delay-kernel constants (see gamma_delay_kernel in cc_eval_warp.cuh for the scheme)
+  {
+    const double sod = par(m.idx_sod), mod = par(m.idx_mod);
+    const double alph = 1.0 / (sod * sod), scale = mod * (sod * sod);
+    constexpr int kTabCap = 12 * 8 * NT - 4;
+    bool fast = (m.gamma_mode == 0) && (alph > 0.0) && (scale > 0.0) && isfinite(alph) && isfinite(scale);
+    double h = 0.0, xT = 0.0, lgam_a = 0.0, lsc = 0.0, QT = 0.0;
+    int km = 0, nser = 0;
+    if (fast) {
+      h = 1.0 / scale;
+      xT = (double)T * h;
+      if (!(h <= 3.6) || !(xT >= 3.0)) fast = false;
+    }
+    if (fast) {
+      const double kmed = fmax(alph - 1.0 / 3.0, 0.0) * scale;
+      km = (kmed >= (double)T) ? T : max((int)ceil(kmed), 16);
+      km = min(km, T);
+      const double x = (double)km * h;
+      const double nstar = fmax(floor(x - alph), 0.0);
+      const double y = 41.5 / x;
+      const double v = y * (1.0 / 3.0) + sqrt(y * y * (1.0 / 9.0) + 2.0 * y);
+      const double nn = nstar + v * x + 4.0;
+      if (!(nn < (double)kTabCap)) fast = false;
+      else nser = (int)nn;
+    }
+    if (fast) {
+      lgam_a = lgamma_shared(alph);
+      lsc = log(scale);
+      if (km < T && xT < alph + 9.0 * sqrt(alph) + 45.0) {
+        // Q(x_T): Legendre continued fraction, forward recurrence
+        double Am1 = 1.0, Ac = xT + 1.0 - alph, Bm1 = 0.0, Bc = 1.0, f = Ac, prev = 0.0;
+        for (int n = 1; n < 600; n++) {
+          const double an = -(double)n * ((double)n - alph), bnn = xT + (double)(2 * n + 1) - alph;
+          const double An = fma(bnn, Ac, an * Am1), Bn = fma(bnn, Bc, an * Bm1);
+          Am1 = Ac; Ac = An; Bm1 = Bc; Bc = Bn;
+          if (fabs(Ac) > 1e200) { Ac *= 1e-200; Am1 *= 1e-200; Bc *= 1e-200; Bm1 *= 1e-200; }
+          if ((n & 1) == 0) {
+            f = Ac / Bc;
+            if (fabs(f - prev) <= 1e-16 * fabs(f)) break;
+            prev = f;
+          }
+        }
+        QT = exp(alph * (m.logk[T] - lsc) - xT - lgam_a) / f;
+      }
+    }
+    put(L.gam + 0, alph); put(L.gam + 1, scale); put(L.gam + 2, h); put(L.gam + 3, lgam_a); put(L.gam + 4, lsc);
+    put(L.gam + 5, (double)km); put(L.gam + 6, (double)nser); put(L.gam + 7, QT); put(L.gam + 8, fast ? 1.0 : 0.0);
+  }
+  // ---- sero constants (binomial.cpp:257-284)
+  {
+    const double rate = par(m.idx_rate);
+    put(L.sero, rate);
+    if (!m.serorev) {
+      const double g1 = -expm1(-1.0 / rate), g32 = -expm1(-32.0 / rate);
+      put(L.sero + 1, g1);
+      put(L.sero + 2, g32);
+      put(L.sero + 3, (g1 == 0.0) ? 0.0 : (1.0 - g1) / g1);
+    } else {
+      const double shape = par(m.idx_shape), wscale = par(m.idx_scale);
+      put(L.sero + 1, shape);
+      put(L.sero + 2, log(wscale));
+      put(L.sero + 3, (!(shape > 0.0) || !(wscale > 0.0)) ? 1.0 : 0.0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ phase 2 pieces
+// delay kernel: w.gs[7 + k] <- P(x_{k+1}) - P(x_k)
+template <int NT>
+__device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const TileSmem& w) {
+  const int lane = threadIdx.x & 31, T = m.T;
+  const double alph = w.rec[L.gam + 0], scale = w.rec[L.gam + 1], h = w.rec[L.gam + 2], lgam_a = w.rec[L.gam + 3],
+               lsc = w.rec[L.gam + 4], QT = w.rec[L.gam + 7];
+  const int km = (int)w.rec[L.gam + 5], nser = (int)w.rec[L.gam + 6];
+  bool fast = w.rec[L.gam + 8] != 0.0;
+  double* P = w.gs + 7;
+  double* tab = w.xs + kXsLead;
+  double* ctab = w.ctab;
+  const double kLogTol = 41.5;
+
+  if (fast && km < T) {
+    // interval-mass table: lane mm holds c_mm = binom(a-1, mm) * gamma(mm+1, h)
+    const int mm = lane;
+    double term = m.rk[mm + 1], sum = term;
+    int j = 1;
+    while (__any_sync(0xffffffffu, term > 1e-18 * sum) && j < 120) {
+      term *= h * m.rk[mm + 1 + j];
+      sum += term;
+      j++;
+    }
+    double hp = h, bn = (mm >= 1) ? (alph - (double)mm) * m.rk[mm] : 1.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t1 = __shfl_up_sync(0xffffffffu, hp, o), t2 = __shfl_up_sync(0xffffffffu, bn, o);
+      if (lane >= o) { hp *= t1; bn *= t2; }
+    }
+    const double emh = exp(-h);
+    double cm = bn * (emh * hp * sum);
+    if (mm == 0) cm = 1.0 - emh;  // gamma(1, h); h is O(0.05..3.6), no cancellation worth an expm1
+    ctab[mm] = cm;
+    const double u1 = scale * m.rk[km + 1];
+    double pw = u1;
+#pragma unroll
+    for (int q = 0; q < 5; q++) pw *= pw;
+    const double c31 = __shfl_sync(0xffffffffu, cm, 31), c0 = __shfl_sync(0xffffffffu, cm, 0);
+    if (!(fabs(c31) * pw <= 1e-18 * c0 * fmin(u1, 1.0)) || !(u1 < 4.0)) fast = false;
+  }
+  if (!fast) {
+    // general algorithm (R's pgamma_raw region split), one day per lane and round
+    const bool bad = isnan(scale) || isnan(alph) || !(scale > 0.0) || alph < 0.0;
+    GammaShape gsh;
+    if (!bad) gsh = gamma_shape(alph);
+    for (int k = lane; k <= T; k += 32) {
+      double v;
+      if (bad) v = (isnan(scale) || isnan(alph)) ? (scale + alph) : d_nan();
+      else v = pgamma_lower(gsh, (double)k / scale);
+      P[k] = v;
+    }
+  } else {
+    for (int n = lane; n <= nser; n += 32) tab[n] = 1.0 / (alph + (double)n);
+    // series lengths of the upper rounds, one per lane: M_r = 2 + 41.5 / log(k0_r / A)
+    const double A = fmax(1.0, fabs(alph - 1.0));
+    int Mr = 32;
+    {
+      const int k0 = km + 1 + 32 * lane;
+      if (k0 < T && (double)k0 > 1.5 * A) Mr = min(32, 2 + (int)(kLogTol / (m.logk[k0] - log(A))));
+    }
+    __syncwarp();
+    // upper part: interval masses, k = km+1 .. T-1, written to P[k]
+    for (int k0 = km + 1, r = 0; k0 < T; k0 += 32, r++) {
+      const int k = k0 + lane;
+      const int M = __shfl_sync(0xffffffffu, Mr, r & 31);
+      const int kc = min(k, T);
+      const double u = scale * m.rk[kc];
+      double I = ctab[M - 1];
+      for (int q = M - 2; q >= 0; q--) I = fma(I, u, ctab[q]);
+      const double f = exp((alph - 1.0) * (m.logk[kc] - lsc) - (double)k * h - lgam_a);
+      if (k < T) P[k] = f * I;
+    }
+    // lower part: series, days 1..km
+    const double lgam_a1 = lgam_a + log(alph);
+    for (int k0 = 1; k0 <= km; k0 += 32) {
+      const int k = k0 + lane;
+      const double x = (double)k * h;
+      double ssum = 1.0;
+      for (int n = nser; n >= 1; n--) ssum = fma(x * tab[n], ssum, 1.0);
+      const double pv = exp(alph * (m.logk[min(k, T)] - lsc) - x - lgam_a1) * ssum;
+      if (k <= km) P[k] = pv;
+    }
+    __syncwarp();
+    // suffix sums of the masses -> Q[k]; P[k] = 1 - Q[k] rounded like the reference's lower-tail value
+    if (km < T) {
+      const int per = (T + 31) >> 5;
+      const int lo = lane * per, hi = min(lo + per, T);
+      double loc = 0.0;
+      for (int k = hi - 1; k >= lo; k--)
+        if (k > km) loc += P[k];
+      double incl = loc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double tnext = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += tnext;
+      }
+      double run = QT + (incl - loc);
+      for (int k = hi - 1; k >= lo; k--)
+        if (k > km) {
+          run += P[k];
+          P[k] = 1.0 - run;
+        }
+      if (lane == 0) P[T] = 1.0 - QT;
+    }
+    if (lane == 0) P[0] = 0.0;
+  }
+  __syncwarp();
+  // differences in place
+  constexpr int kPer = 2 * NT;
+  double dgv[kPer];
+#pragma unroll
+  for (int u = 0; u < kPer; u++) {
+    const int k = lane + 32 * u;
+    dgv[u] = (k < T) ? (P[k + 1] - P[k]) : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < kPer; u++) P[lane + 32 * u] = dgv[u];
+  if (lane < 9) P[64 * NT + lane] = 0.0;
+  __syncwarp();
+}
+
+// w.sk[k] <- CH[k] = sum_{u<k} H[u], k = 0..M  (binomial.cpp:257-284)
+template <int NT>
+__device__ inline void tile_sero_prefix(const KModel& m, const RecLayout& L, const TileSmem& w) {
+  const int lane = threadIdx.x & 31, M = m.M;
+  const double rate = w.rec[L.sero];
+  if (!m.serorev) {
+    const double g1 = w.rec[L.sero + 1], g32 = w.rec[L.sero + 2], fac = w.rec[L.sero + 3];
+    double gk = -expm1(-(double)lane / rate);
+    for (int k = lane; k <= M; k += 32) {
+      w.sk[k] = (g1 == 0.0) ? 0.0 : ((double)k - fac * gk);
+      gk = fma(-gk, g32, gk + g32);
+    }
+    __syncwarp();
+    return;
+  }
+  const double shape = w.rec[L.sero + 1], lws = w.rec[L.sero + 2];
+  const bool badw = w.rec[L.sero + 3] != 0.0;
+  const double rr = 1.0 / rate;
+  for (int k = lane; k < 64 * NT; k += 32) {
+    double c = 0.0, sv = 0.0;
+    if (k < M) {
+      c = rr * exp(-(double)(k + 1) / rate);
+      sv = badw ? d_nan() : ((k == 0) ? 1.0 : exp(-exp(shape * (m.logk[k] - lws))));
+    }
+    w.xs[xs_index(k)] = c;
+    w.gs[7 + k] = sv;
+  }
+  if (lane < 9) w.gs[7 + 64 * NT + lane] = 0.0;
+  __syncwarp();
+  double acc[NT][2];
+  toeplitz_dmma<NT>(w.xs, w.gs, (M + 7) >> 3, acc);
+  __syncwarp();
+  double* haz = w.gs + 8;
+  {
+    const int n = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int P = 0; P < NT; P++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int j = 64 * P + 16 * t + 8 * e + n;
+        haz[j] = (j < M) ? acc[P][e] : 0.0;
+      }
+  }
+  __syncwarp();
+  const int per = (M + 31) >> 5;
+  const int lo = min(lane * per, M), hi = min(lo + per, M);
+  double loc = 0.0;
+  for (int u = lo; u < hi; u++) loc += haz[u];
+  double incl = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double tprev = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += tprev;
+  }
+  double run = incl - loc;
+  for (int u = lo; u < hi; u++) {
+    w.sk[u] = run;
+    run += haz[u];
+  }
+  if (hi == M && lo < M) w.sk[M] = run;
+  __syncwarp();
+}
+
+// reduce four values at once (one shuffle loop in the instruction stream)
+__device__ __forceinline__ void warp_sum4(double& a, double& b, double& c, double& d) {
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+}
+
+// phase 2 for vector e of the tile: per-day stages; writes o_status, o_l1, o_texpd, o_sunc, o_base[S] to the scratch
+template <int NT>
+__device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, double* __restrict__ scr, int e) {
+  const int lane = threadIdx.x & 31, T = m.T, A = m.A, S = m.S;
+  __syncwarp();
+  for (int f = lane; f < L.n2; f += 32) w.rec[f] = scr[f * 32 + e];
+  __syncwarp();
+  if (w.rec[L.flags] == 0.0) return;  // knots not increasing: phase 3 returns the failure value
+
+  tile_sero_prefix<NT>(m, L, w);   // S10 (first: with seroreversion it borrows the series/kernel regions)
+  tile_gamma<NT>(m, L, w);         // S2
+
+  // ---- S5 infection curve + S6 population check
+  double tot = 0.0;
+  {
+    const int K = m.K;
+    for (int i = lane; i < 64 * NT; i += 32) {
+      double v = 0.0;
+      if (i < T) {
+        int j = 0;
+        const double di = (double)i;
+        for (int mI = 0; mI < K - 2; mI++) j += (w.rec[L.cday + mI] < di) ? 1 : 0;
+        const double* c = w.rec + L.spl + 5 * j;
+        const double dx = (double)(i + 1) - c[0];
+        const double y = (i == 0) ? w.rec[L.spl + 1] : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
+        v = exp(y);
+        tot += v;
+      }
+      w.xs[xs_index(i)] = v;
+    }
+  }
+  tot = warp_sum(tot);
+  {
+    bool ok = true;
+    for (int a = lane; a < A; a += 32) ok = ok && !(w.rec[L.ne + a] * tot > (double)m.demog[a]);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) scr[L.o_status * 32 + e] = ok ? 0.0 : 1.0;
+    if (!ok) return;
+  }
+  __syncwarp();
+
+  // ---- S7 death-delay convolution on the tensor cores, then back to day order through shared memory
+  {
+    double auc[NT][2];
+    toeplitz_dmma<NT>(w.xs, w.gs, (T + 7) >> 3, auc);
+    __syncwarp();
+    const int n = lane >> 2, t = lane & 3;
+    double* aucs = w.gs + 8;
+#pragma unroll
+    for (int P = 0; P < NT; P++) {
+      aucs[64 * P + 16 * t + n] = auc[P][0];
+      aucs[64 * P + 16 * t + 8 + n] = auc[P][1];
+    }
+  }
+  __syncwarp();
+
+  // ---- S8 Poisson term
+  double l1 = 0.0, s_all = 0.0, s_unc = 0.0, dummy = 0.0;
+  {
+    const double snm = w.rec[L.snm];
+    const double* aucs = w.gs + 8;
+    for (int j = lane; j < T; j += 32) {
+      const double a = aucs[j];
+      const double expd = a * snm;
+      s_all += expd;
+      if ((j + 1) < m.rcensor_day) {
+        s_unc += a;
+        const int x = m.obsd[j];
+        if (x != -1) {
+          double lp;
+          if (!(expd >= 0.0)) lp = d_nan();        // NaN or negative mean -> NaN (R::dpois)
+          else if (x < 0) lp = -d_inf();
+          else if (x == 0) lp = -expd;
+          else lp = (double)x * log(expd) - expd;  // - lgamma(x+1) is data only: m.l1_const
+          l1 += lp;
+        }
+      }
+    }
+  }
+  warp_sum4(l1, s_all, s_unc, dummy);
+  if (lane == 0) {
+    scr[L.o_l1 * 32 + e] = l1 - m.l1_const;
+    scr[L.o_texpd * 32 + e] = s_all;
+    scr[L.o_sunc * 32 + e] = s_unc;
+  }
+
+  // ---- S11/S12 survey-window means of infxn (*) H through the prefix-summed hazard
+  for (int s = 0; s < S; s++) {
+    const int st = m.sero_start[s], en = m.sero_end[s];
+    double b = 0.0;
+    for (int t = lane; t < en; t += 32) {
+      int lo = st - 1 - t;
+      lo = lo < 0 ? 0 : lo;
+      b = fma(w.xs[xs_index(t)], w.sk[en - t] - w.sk[lo], b);
+    }
+    b = warp_sum(b);
+    if (lane == 0) scr[(L.o_base + s) * 32 + e] = b / (double)(en - st + 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ phase 3
+// G = 32 / E lanes cooperate on one vector: lane = sub * E + e; terms are strided over sub and xor-reduced over the high bits
+__device__ inline double tile_phase3(const KModel& m, const RecLayout& L, const double* __restrict__ scr, int e, int sub, int G, int E) {
+  const int A = m.A, S = m.S;
+  auto get = [&](int f) { return scr[f * 32 + e]; };
+  const bool pass = get(L.flags) != 0.0 && get(L.o_status) == 0.0;
+  double tail = 0.0;
+  if (pass) {
+    const double texpd = get(L.o_texpd), sum_unc = get(L.o_sunc);
+    // S9: chained binomial on the age split (binomial.cpp:227-251), running subtraction in the reference's order
+    for (int a = sub; a < A - 1; a += G) {
+      double te = texpd;
+      for (int b = 0; b < a; b++) te -= get(L.nm + b) * sum_unc;
+      tail += dbinom_log_shared(round(get(L.nm + a) * sum_unc), round(te), m.l2_prob[a]);
+    }
+    // S13: serology
+    const double sens = get(L.sens), spec = get(L.spec);
+    for (int k = sub; k < S * A; k += G) {
+      const int s = k / A, a = k - s * A;
+      const double frac = (get(L.ne + a) * get(L.o_base + s)) / (double)m.demog[a];
+      const double prev = sens * frac + (1 - spec) * (1 - frac);
+      if (m.binomial) {
+        const int kind = m.l3_kind[k];
+        if (kind == 1) {
+          const double x = m.sero_a[k], nn = m.sero_b[k];
+          double v;
+          if (!(prev >= 0.0 && prev <= 1.0)) v = d_nan();
+          else if (x == 0.0) v = (nn == 0.0) ? 0.0 : nn * log(1 - prev);
+          else if (x == nn) v = nn * log(prev);
+          else v = m.l3_lchoose[k] + x * log(prev) + (nn - x) * log(1 - prev);
+          tail += v;
+        } else if (kind == 2) {
+          tail += dbinom_log_shared(m.sero_a[k], m.sero_b[k], prev);
+        }
+      } else {
+        const double eps = DBL_MIN / 100.0;
+        const double lg = log((prev + eps) / (1 - (prev + eps)));
+        tail += dnorm_log(lg, m.sero_a[k], m.sero_b[k]);
+      }
+    }
+  }
+  for (int o = E; o < 32; o <<= 1) tail += __shfl_xor_sync(0xffffffffu, tail, o);
+  if (!pass) return -CC_OVERFLO;
+  double loglik = get(L.o_l1) + tail;
+  if (!isfinite(loglik)) loglik = -CC_OVERFLO;
+  return loglik;
+}
+
+// generated logprior for E vectors per warp: G lanes per vector, terms strided over sub (Agecpp2strings.R:66-219)
+template <typename Par>
+__device__ inline double tile_logprior(const KModel& m, int sub, int G, int E, Par par) {
+  double v = 0.0;
+  for (int i = sub; i < m.d; i += G) {
+    const int fam = m.prior_family[i];
+    if (fam != CC_PRIOR_NONE) {
+      const double x = par(i), a = m.prior_p1[i], b = m.prior_p2[i];
+      v += (fam == CC_PRIOR_DUNIF) ? dunif_log(x, a, b) : (fam == CC_PRIOR_DNORM) ? dnorm_log(x, a, b) : dbeta_log(x, a, b);
+    }
+  }
+  for (int j = sub; j < 3; j += G)
+    if (m.jac_rows[j] >= 0) v += m.jac_counts[j] * log(par(max(m.jac_rows[j], 0)));
+  for (int o = E; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (!isfinite(v)) v = -CC_OVERFLO;
+  return v;
+}
+
+}  // namespace ccdev

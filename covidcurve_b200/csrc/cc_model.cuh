@@ -28,12 +28,19 @@ struct KModel {
   double l2_prob[CC_MAX_STRATA];   // paobsd[a] / (running paobsd_sum), binomial.cpp:248-250 (data only)
   int sero_start[CC_MAX_SEROSURVEYS];
   int sero_end[CC_MAX_SEROSURVEYS];
+  int debug_stop;                  // developer switch (CC_DEBUG_STOP): stop the evaluation after stage n (0 = run everything)
+  int gamma_mode;                  // 0: fast shared-shape evaluation with fallback, 1: always the general (R region-split) algorithm
   int jac_rows[3];
   double jac_counts[3];
   // device tables
   const int* obsd;        // [T] observed deaths as int, -1 = missing (binomial.cpp:204)
   const double* pois_c;   // [T] -0.5*log(2*pi*x) - stirlerr(x) for x > 0, else 0   (x-only part of dpois)
   const double* lgx1;     // [T] lgamma(x+1)
+  const double* logk;     // [T+1] log(k), k >= 1 (entry 0 unused): log of the integer days / lags
+  const double* rk;       // [max(T,160)+2] 1/k, k >= 1
+  double l1_const;        // sum of lgamma(x+1) over the days that enter L1 (uncensored, observed, x >= 0)
+  const int* l3_kind;     // [S*A] 0: skipped (pos == n == -1), 1: regular counts, 2: irregular -> R's full dbinom case analysis
+  const double* l3_lchoose;  // [S*A] lchoose(n, pos) for regular counts
   const double* sero_a;   // [S*A]
   const double* sero_b;   // [S*A]
   const double* pmin;     // [d]
@@ -61,4 +68,8 @@ struct cc_model {
   double* d_out = nullptr; size_t d_out_bytes = 0;
   std::vector<double> pinit;
   int sm_count = 0;
+  int grid_max = 1;                // resident CTAs of the evaluation kernel on this device
+  double* scratch[3] = {nullptr, nullptr, nullptr};  // record tiles: [0] device-pointer calls, [1],[2] the two host-path streams
+  size_t scratch_doubles = 0;
+  int nt = 0;                      // 64-day output tiles per evaluation (template parameter of the warp kernels)
 };

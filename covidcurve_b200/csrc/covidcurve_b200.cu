@@ -9,6 +9,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -16,6 +17,8 @@
 
 #include "../../include/covidcurve_b200.h"
 #include "cc_eval.cuh"
+#include "cc_eval_warp.cuh"
+#include "cc_eval_tile.cuh"
 #include "cc_mcmc_dev.cuh"
 #include "cc_model.cuh"
 
@@ -47,6 +50,160 @@ extern "C" int cc_device_count(void) {
 
 // ------------------------------------------------------------------------------------------------ kernels
 constexpr int kEvalThreads = 128;
+
+constexpr int kWarpsPerCta = 4;
+
+// Tile-phased evaluation (cc_eval_tile.cuh): each warp walks tiles of 32 consecutive parameter vectors.
+// theta is structure-of-arrays [d][ld]; scratch holds one record tile (F x 32 doubles) per warp of the grid.
+template <int NT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) loglike_tile_kernel(const KModel m, const double* __restrict__ theta, long long n,
+                                                                          long long ld, double* __restrict__ out, double* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RecLayout L = rec_layout(m.K, m.A, m.S);
+  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
+  tile_smem_init(w);
+  const long long gwarp = (long long)blockIdx.x * kWarpsPerCta + warp, nwarps = (long long)gridDim.x * kWarpsPerCta;
+  double* scr = scratch + (size_t)gwarp * L.F * 32;
+  for (long long v0 = gwarp * 32; v0 < n; v0 += nwarps * 32) {
+    const long long v = v0 + lane;
+    if (v < n) tile_phase1<NT>(m, L, scr, lane, [&](int i) { return theta[(long long)i * ld + v]; });
+    __syncwarp();
+    const int cnt = (int)min((long long)32, n - v0);
+    for (int e = 0; e < cnt; e++) tile_phase2<NT>(m, L, w, scr, e);
+    __syncwarp();
+    const double ll = tile_phase3(m, L, scr, lane, 0, 1, 32);
+    if (v < n) out[v] = ll;
+    __syncwarp();
+  }
+}
+
+// decode lane -> (vector e of the tile, sub-lane) for tiles of E = 2^le vectors
+struct TileLane { int e, sub, G, E; };
+__device__ __forceinline__ TileLane tile_lane(int le) {
+  TileLane t;
+  const int lane = threadIdx.x & 31;
+  t.E = 1 << le;
+  t.G = 32 >> le;
+  t.e = lane & (t.E - 1);
+  t.sub = lane >> le;
+  return t;
+}
+
+// initial state of every particle: phi, loglike, logprior
+template <int NT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_init_tile_kernel(const KModel m, const McmcState s, int le, double* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const RecLayout L = rec_layout(m.K, m.A, m.S);
+  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
+  tile_smem_init(w);
+  const TileLane tl = tile_lane(le);
+  const int gwarp = blockIdx.x * kWarpsPerCta + warp, nwarps = gridDim.x * kWarpsPerCta;
+  double* scr = scratch + (size_t)gwarp * L.F * 32;
+  const int P = s.n_chains * s.rungs, d = m.d;
+  for (int p0 = gwarp * tl.E; p0 < P; p0 += nwarps * tl.E) {
+    const int p = p0 + tl.e;
+    const bool valid = p < P;
+    const double* th = s.theta + (size_t)(valid ? p : 0) * d;
+    auto par = [&](int j) { return th[j]; };
+    if (valid)
+      for (int i = tl.sub; i < d; i += tl.G) {
+        const double lo = m.pmin[i], hi = m.pmax[i];
+        s.phi[(size_t)p * d + i] = theta_to_phi(trans_type(lo, hi), th[i], lo, hi);
+      }
+    if (valid && tl.sub == 0) tile_phase1<NT>(m, L, scr, tl.e, par);
+    __syncwarp();
+    const int cnt = min(tl.E, P - p0);
+    for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, scr, q);
+    __syncwarp();
+    const double ll = tile_phase3(m, L, scr, tl.e, tl.sub, tl.G, tl.E);
+    const double lp = tile_logprior(m, tl.sub, tl.G, tl.E, par);
+    if (valid && tl.sub == 0) {
+      s.ll[p] = ll;
+      s.lp[p] = lp;
+    }
+    __syncwarp();
+  }
+}
+
+// One sweep of d single-site Metropolis-Hastings updates for every (chain, rung); a warp owns E = 2^le particles.
+// `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
+template <int NT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_tile_kernel(const KModel m, const McmcState s, int iteration, int le,
+                                                                             double* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const RecLayout L = rec_layout(m.K, m.A, m.S);
+  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
+  tile_smem_init(w);
+  const TileLane tl = tile_lane(le);
+  const int gwarp = blockIdx.x * kWarpsPerCta + warp, nwarps = gridDim.x * kWarpsPerCta;
+  double* scr = scratch + (size_t)gwarp * L.F * 32;
+  const int d = m.d;
+  const int P = s.n_chains * s.rungs;
+  const bool adapt = s.adapt_in_sampling || iteration <= s.burnin;
+  for (int b0 = gwarp * tl.E; b0 < P; b0 += nwarps * tl.E) {
+    const int b = min(b0 + tl.e, P - 1);
+    const bool valid = (b0 + tl.e) < P;
+    const int c = b / s.rungs, r = b - c * s.rungs;
+    const int pid = s.at_rung[b];  // particle (within chain) sitting at rung position r
+    const int p = c * s.rungs + pid;
+    const int slot = s.bw_per_particle ? p : b;
+    const double beta = s.beta[r];
+    double* th = s.theta + (size_t)p * d;
+    double* ph = s.phi + (size_t)p * d;
+    double* bw = s.bw + (size_t)slot * d;
+    int* bwi = s.bw_index + (size_t)slot * d;
+    unsigned int* macc = s.move_acc + (size_t)b * d;
+    double ll = s.ll[p], lp = s.lp[p];
+    const int cnt = min(tl.E, P - b0);
+    for (int i = 0; i < d; i++) {
+      // every lane of the particle's group computes the (cheap) proposal redundantly
+      const ccrng::Draw dr = ccrng::draw(s.seed, ccrng::kStreamMove, (uint32_t)(s.chain_offset + c), (uint32_t)pid,
+                                         (uint32_t)iteration, (uint32_t)i);
+      const double lo = m.pmin[i], hi = m.pmax[i];
+      const int tt = trans_type(lo, hi);
+      const double th_old = th[i];
+      const double bwv = bw[i];
+      const double php = ph[i] + bwv * dr.z;
+      const double thp = phi_to_theta(tt, php, lo, hi);
+      const double adj = mh_adjust(tt, th_old, thp, lo, hi);
+      auto par = [&](int j) { return j == i ? thp : th[j]; };
+      if (valid && tl.sub == 0) tile_phase1<NT>(m, L, scr, tl.e, par);
+      __syncwarp();
+      for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, scr, q);
+      __syncwarp();
+      const double llp = tile_phase3(m, L, scr, tl.e, tl.sub, tl.G, tl.E);
+      const double lpp = tile_logprior(m, tl.sub, tl.G, tl.E, par);
+      const double mh = beta * (llp - ll) + (lpp - lp) + adj;
+      const bool acc = log(dr.u) < mh;  // uniform over the particle's lane group
+      if (acc) {
+        ll = llp;
+        lp = lpp;
+      }
+      __syncwarp();
+      if (valid && tl.sub == 0) {
+        if (acc) {
+          th[i] = thp;
+          ph[i] = php;
+          macc[i] += 1u;
+        }
+        if (adapt) {
+          // Robbins-Monro on log(bw) towards a 0.234 acceptance rate
+          const double step = acc ? (1.0 - 0.234) : -0.234;
+          bw[i] = exp(log(bwv) + step / sqrt((double)bwi[i]));
+          bwi[i] += 1;
+        }
+      }
+      __syncwarp();
+    }
+    if (valid && tl.sub == 0) {
+      s.ll[p] = ll;
+      s.lp[p] = lp;
+    }
+  }
+}
 
 // One CTA per parameter vector; theta is structure-of-arrays [d][ld].
 __global__ void __launch_bounds__(kEvalThreads) loglike_batch_kernel(const KModel m, const double* __restrict__ theta,
@@ -269,9 +426,6 @@ __global__ void fp64_probe_kernel(double* out, int iters, double a, double b) {
 
 // ---- FP64 tensor-core (DMMA m8n8k4) probe, optionally interleaved with independent DFMA chains, to learn whether
 // the two share a pipe on this part (decides where the Toeplitz contraction should run).
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 template <int NFMA>
 __global__ void dmma_probe_kernel(double* out, int iters, double a, double b) {
   double c[8][2];
@@ -293,6 +447,32 @@ __global__ void dmma_probe_kernel(double* out, int iters, double a, double b) {
 #pragma unroll
   for (int u = 0; u < 8; u++) sum += c[u][0] + c[u][1] + x[u];
   if (sum == 123.456) out[0] = sum;
+}
+
+// ------------------------------------------------------------------------------------------------ warp-kernel dispatch
+// NT = number of 64-day output tiles per evaluation; instantiated for the shapes in use (T <= 64 NT)
+#define CC_FOR_EACH_NT(X) X(4) X(5) X(7) X(16)
+static int pick_nt(int T) {
+  const int need = warp_tiles(T);
+#define CC_PICK(NT_) if (need <= NT_) return NT_;
+  CC_FOR_EACH_NT(CC_PICK)
+#undef CC_PICK
+  return -1;
+}
+static size_t warp_cta_smem(const KModel& k, int nt) { return (size_t)kWarpsPerCta * tile_smem_doubles(k.K, k.A, k.S, nt) * sizeof(double); }
+
+static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
+  const int bytes = (int)warp_cta_smem(k, nt);
+  cudaError_t e = cudaSuccess;
+#define CC_OPT(NT_)                                                                                                   \
+  if (nt == NT_) {                                                                                                    \
+    e = cudaFuncSetAttribute(loglike_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+  }
+  CC_FOR_EACH_NT(CC_OPT)
+#undef CC_OPT
+  return e;
 }
 
 // ------------------------------------------------------------------------------------------------ model
@@ -373,18 +553,25 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   KModel& k = m->k;
   k.d = d; k.A = A; k.K = K; k.T = T; k.S = S; k.M = M;
   k.rcensor_day = de->rcensor_day;
+  {
+    const char* gm = std::getenv("CC_GAMMA_MODE");  // developer switch: 1 = always use the general incomplete-gamma algorithm
+    k.gamma_mode = (gm && gm[0] == '1') ? 1 : 0;
+    const char* ds = std::getenv("CC_DEBUG_STOP");
+    k.debug_stop = ds ? std::atoi(ds) : 0;
+  }
   k.serorev = de->account_serorev ? 1 : 0;
   k.binomial = de->binomial_likelihood ? 1 : 0;
   k.reparam_ifr = de->reparam_ifr ? 1 : 0;
   k.reparam_knots = de->reparam_knots ? 1 : 0;
   k.reparam_infxn = de->reparam_infxn ? 1 : 0;
   k.idx_sens = de->idx_sens; k.idx_spec = de->idx_spec; k.idx_rate = de->idx_sero_con_rate;
-  k.idx_shape = de->account_serorev ? de->idx_sero_rev_shape : -1;
-  k.idx_scale = de->account_serorev ? de->idx_sero_rev_scale : -1;
+  // unused role rows are 0, not -1: the flags decide whether they are read, and a compiler-speculated load stays in bounds
+  k.idx_shape = de->account_serorev ? de->idx_sero_rev_shape : 0;
+  k.idx_scale = de->account_serorev ? de->idx_sero_rev_scale : 0;
   k.idx_mod = de->idx_mod; k.idx_sod = de->idx_sod;
-  k.idx_rel_knot = de->reparam_knots ? de->idx_rel_knot : -1;
-  k.idx_rel_infxn = de->reparam_infxn ? de->idx_rel_infxn : -1;
-  k.idx_max_ma = de->reparam_ifr ? de->idx_max_ma : -1;
+  k.idx_rel_knot = de->reparam_knots ? de->idx_rel_knot : 0;
+  k.idx_rel_infxn = de->reparam_infxn ? de->idx_rel_infxn : 0;
+  k.idx_max_ma = de->reparam_ifr ? de->idx_max_ma : 0;
   for (int i = 0; i < K - 1; i++) k.idx_knots[i] = (short)de->idx_knots[i];
   for (int i = 0; i < K; i++) k.idx_infxn[i] = (short)de->idx_infxn[i];
   for (int a = 0; a < A; a++) {
@@ -421,12 +608,33 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
     pois_c[i] = (x > 0) ? (-0.5 * std::log(CC_2PI * x) - host_stirlerr(x)) : 0.0;
     lgx1[i] = (x >= 0) ? std::lgamma(x + 1.0) : 0.0;
   }
+  std::vector<double> logk(T + 1, 0.0);
+  for (int i = 1; i <= T; i++) logk[i] = std::log((double)i);
+  std::vector<double> rk(std::max(T, 160) + 2, 0.0);
+  for (size_t i = 1; i < rk.size(); i++) rk[i] = 1.0 / (double)i;
+  {
+    long double c = 0.0L;
+    for (int i = 0; i < T; i++)
+      if ((i + 1) < k.rcensor_day && obsd[i] >= 0) c += lgammal((long double)obsd[i] + 1.0L);
+    k.l1_const = (double)c;
+  }
   std::vector<double> sa(de->sero_a, de->sero_a + (size_t)S * A), sb(de->sero_b, de->sero_b + (size_t)S * A);
+  std::vector<int> l3_kind((size_t)S * A, 0);
+  std::vector<double> l3_lch((size_t)S * A, 0.0);
+  for (size_t q = 0; q < (size_t)S * A; q++) {
+    const double x = sa[q], nn = sb[q];
+    if (x == -1 && nn == -1) l3_kind[q] = 0;  // binomial.cpp:334
+    else if (std::isfinite(x) && std::isfinite(nn) && x == std::floor(x) && nn == std::floor(nn) && x >= 0 && x <= nn && nn < 9e15) {
+      l3_kind[q] = 1;
+      l3_lch[q] = (double)(lgammal((long double)nn + 1.0L) - lgammal((long double)x + 1.0L) - lgammal((long double)(nn - x) + 1.0L));
+    } else l3_kind[q] = 2;
+  }
   std::vector<double> pmin(de->pmin, de->pmin + d), pmax(de->pmax, de->pmax + d);
   std::vector<int> fam(de->prior_family, de->prior_family + d);
   std::vector<double> p1(de->prior_p1, de->prior_p1 + d), p2(de->prior_p2, de->prior_p2 + d);
   int rc = CC_OK;
   if ((rc = upload(m, obsd, &k.obsd)) || (rc = upload(m, pois_c, &k.pois_c)) || (rc = upload(m, lgx1, &k.lgx1)) ||
+      (rc = upload(m, logk, &k.logk)) || (rc = upload(m, rk, &k.rk)) || (rc = upload(m, l3_kind, &k.l3_kind)) || (rc = upload(m, l3_lch, &k.l3_lchoose)) ||
       (rc = upload(m, sa, &k.sero_a)) || (rc = upload(m, sb, &k.sero_b)) || (rc = upload(m, pmin, &k.pmin)) ||
       (rc = upload(m, pmax, &k.pmax)) || (rc = upload(m, fam, &k.prior_family)) || (rc = upload(m, p1, &k.prior_p1)) ||
       (rc = upload(m, p2, &k.prior_p2))) {
@@ -438,14 +646,33 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
   for (int q = 0; q < 2 && e == cudaSuccess; q++) e = cudaEventCreateWithFlags(&m->ev_stage[q], cudaEventDisableTiming);
-  // opt in to large dynamic shared memory once (T up to CC_MAX_DAYS needs > 48 KB)
-  const size_t smem = eval_smem_bytes(d, T, T);
-  if (e == cudaSuccess && smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(loglike_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(curves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // opt in to large dynamic shared memory once
+  m->nt = pick_nt(T);
+  if (e == cudaSuccess && m->nt < 0) {
+    cc_model_destroy(m);
+    return fail(CC_E_INVALID, "days_obsd too large for the instantiated kernels");
   }
+  if (e == cudaSuccess) e = warp_kernels_opt_in(k, m->nt);
+  if (e == cudaSuccess) {
+    int bps = 0;
+    const size_t sm_bytes = warp_cta_smem(k, m->nt);
+    switch (m->nt) {
+#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_tile_kernel<NT_>, 32 * kWarpsPerCta, sm_bytes); break;
+      CC_FOR_EACH_NT(CC_OCC)
+#undef CC_OCC
+      default: break;
+    }
+    if (e == cudaSuccess && bps < 1) {
+      cc_model_destroy(m);
+      return fail(CC_E_INVALID, "model too large for one CTA's shared memory");
+    }
+    m->grid_max = std::max(1, bps) * m->sm_count;
+    const RecLayout L = rec_layout(K, A, S);
+    m->scratch_doubles = (size_t)m->grid_max * kWarpsPerCta * L.F * 32;
+    for (int q = 0; q < 3 && e == cudaSuccess; q++) e = cudaMalloc((void**)&m->scratch[q], m->scratch_doubles * sizeof(double));
+  }
+  const size_t smem = eval_smem_bytes(d, T, T);
+  if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(curves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     cc_model_destroy(m);
     return fail(CC_E_CUDA, std::string("cc_model_create: ") + cudaGetErrorString(e));
@@ -458,6 +685,8 @@ extern "C" void cc_model_destroy(cc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   for (void* p : m->dev_allocs) cudaFree(p);
+  for (int q = 0; q < 3; q++)
+    if (m->scratch[q]) cudaFree(m->scratch[q]);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->d_out) cudaFree(m->d_out);
   if (m->h_pin) cudaFreeHost(m->h_pin);
@@ -471,16 +700,24 @@ extern "C" void cc_model_destroy(cc_model* m) {
 }
 
 // ------------------------------------------------------------------------------------------------ batch calls
-static int launch_loglike(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st) {
+static int launch_loglike(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st, int slot) {
   const KModel& k = m->k;
-  const size_t smem = eval_smem_bytes(k.d, k.T, k.M);
-  const long long grid = std::min<long long>(n, 0x7fffffffLL);
-  loglike_batch_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(k, d_theta, n, ld, d_out);
+  const size_t smem = warp_cta_smem(k, m->nt);
+  const long long tiles = (n + 31) / 32;
+  const long long ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned grid = (unsigned)std::min<long long>(ctas, (long long)m->grid_max);
+  double* scr = m->scratch[slot];
+  switch (m->nt) {
+#define CC_LAUNCH(NT_) case NT_: loglike_tile_kernel<NT_><<<grid, 32 * kWarpsPerCta, smem, st>>>(k, d_theta, n, ld, d_out, scr); break;
+    CC_FOR_EACH_NT(CC_LAUNCH)
+#undef CC_LAUNCH
+    default: return fail(CC_E_INVALID, "unsupported days_obsd for the instantiated kernels");
+  }
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
-static int launch_logprior(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st) {
+static int launch_logprior(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st, int /*slot*/) {
   const int bs = 128;
   const long long grid = (n + bs - 1) / bs;
   logprior_batch_kernel<<<(unsigned)grid, bs, 0, st>>>(m->k, d_theta, n, ld, d_out);
@@ -506,7 +743,7 @@ static int ensure_stage(cc_model* m, size_t theta_bytes, size_t out_bytes) {
   return CC_OK;
 }
 
-typedef int (*launch_fn)(cc_model*, const double*, long long, long long, double*, cudaStream_t);
+typedef int (*launch_fn)(cc_model*, const double*, long long, long long, double*, cudaStream_t, int);
 
 // Host-buffer path: column chunks are copied H2D (2-D copy: d rows of `chunk` doubles), evaluated and copied back,
 // double-buffered over two streams so that copies overlap the kernel.  Pinned caller memory gives true overlap;
@@ -527,7 +764,7 @@ static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long l
     double* dout = m->d_out + (size_t)q * chunk;
     CC_CUDA(cudaMemcpy2DAsync(dth, (size_t)chunk * sizeof(double), theta + c0, (size_t)ld * sizeof(double),
                               (size_t)cn * sizeof(double), (size_t)d, cudaMemcpyHostToDevice, st[q]));
-    rc = fn(m, dth, cn, chunk, dout, st[q]);
+    rc = fn(m, dth, cn, chunk, dout, st[q], 1 + q);
     if (rc) return rc;
     m->last_launches++;
     CC_CUDA(cudaMemcpyAsync(out + c0, dout, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost, st[q]));
@@ -551,7 +788,7 @@ static int batch_call(cc_model* m, launch_fn fn, const double* theta, int64_t n,
   if (mem == CC_MEM_DEVICE) {
     cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
     CC_CUDA(cudaEventRecord(m->ev0, st));
-    int rc = fn(m, theta, n, ld, out, st);
+    int rc = fn(m, theta, n, ld, out, st, 0);
     if (rc) return rc;
     CC_CUDA(cudaEventRecord(m->ev1, st));
     m->last_launches = 1;
@@ -637,6 +874,9 @@ struct cc_mcmc {
   long long rows = 0;
   long long evals = 0;
   size_t smem = 0;
+  int le = 0;          // log2 of the particles per warp tile
+  unsigned grid = 1;
+  double* scratch = nullptr;
 };
 
 template <typename T>
@@ -746,8 +986,27 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
       return fail(CC_E_CUDA, std::string("cc_mcmc_create: ") + cudaGetErrorString(e));
     }
   }
-  r->smem = eval_smem_bytes(d, m->k.T, m->k.M);
-  mcmc_init_kernel<<<(unsigned)P, kEvalThreads, r->smem, m->stream>>>(m->k, s);
+  r->smem = warp_cta_smem(m->k, m->nt);
+  {
+    // particles per warp tile: as many as keep every warp slot of the GPU busy (E = 1 for small runs)
+    const long long slots = (long long)m->grid_max * kWarpsPerCta;
+    int le = 5;
+    while (le > 0 && (long long)((P + (1u << le) - 1) >> le) < slots) le--;
+    r->le = le;
+    const long long tiles = ((long long)P + (1 << le) - 1) >> le;
+    r->grid = (unsigned)std::min<long long>((tiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)m->grid_max);
+    const RecLayout L = rec_layout(m->k.K, m->k.A, m->k.S);
+    if ((rc = dalloc(r, &r->scratch, (size_t)r->grid * kWarpsPerCta * L.F * 32, false))) {
+      cc_mcmc_destroy(r);
+      return rc;
+    }
+    switch (m->nt) {
+#define CC_LAUNCH(NT_) case NT_: mcmc_init_tile_kernel<NT_><<<r->grid, 32 * kWarpsPerCta, r->smem, m->stream>>>(m->k, s, r->le, r->scratch); break;
+      CC_FOR_EACH_NT(CC_LAUNCH)
+#undef CC_LAUNCH
+      default: break;
+    }
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     cc_mcmc_destroy(r);
@@ -779,7 +1038,12 @@ extern "C" int cc_mcmc_advance(cc_mcmc* r, int32_t n_iter) {
   for (int k = 0; k < n_iter; k++) {
     if (r->iteration >= total) return fail(CC_E_STATE, "cc_mcmc_advance: burnin + samples iterations already done");
     const int it = (int)(r->iteration + 1);
-    mcmc_sweep_kernel<<<P, kEvalThreads, r->smem, m->stream>>>(m->k, s, it);
+    switch (m->nt) {
+#define CC_LAUNCH(NT_) case NT_: mcmc_sweep_tile_kernel<NT_><<<r->grid, 32 * kWarpsPerCta, r->smem, m->stream>>>(m->k, s, it, r->le, r->scratch); break;
+      CC_FOR_EACH_NT(CC_LAUNCH)
+#undef CC_LAUNCH
+      default: break;
+    }
     CC_CUDA(cudaGetLastError());
     r->evals += (long long)P * s.d;
     int rc = record_and_swap(r, it, 1);

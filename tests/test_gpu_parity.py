@@ -94,7 +94,7 @@ def test_early_exits_and_non_finite_inputs(built_lib, modfit):
     th[2, ix["y5"]] = 30.0                         # more infections than people
     th[3, ix["sod"]] = np.nan
     th[4, ix["ma1"]] = -0.1                        # negative Poisson mean -> NaN -> clamp
-    th[5, ix["sens"]] = 50.0                       # p outside [0,1] -> NaN -> clamp
+    th[5, ix["spec"]] = -5.0                      # p outside [0,1] -> NaN -> clamp
     th[6, ix["x1"]] = 2.0000001; th[6, ix["x2"]] = 2.5   # two knots inside one day (interval-lag rule)
     th[7, ix["sod"]] = 1.7                         # shape < 1 (continued-fraction branch of pgamma)
     got, want = _model(spec).loglike(th), _oracle(spec).loglike(th)
