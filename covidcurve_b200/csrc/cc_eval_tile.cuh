@@ -48,11 +48,11 @@ struct TileSmem {
   double* xs;   // padded series
   double* gs;   // kernel / later the convolution output in day order
   double* sk;   // CH prefix sums
-  double* ctab; // [32]
+  double* ctab; // [128] interval-mass coefficients
 };
 __host__ __device__ inline size_t tile_smem_doubles(int K, int A, int S, int NT) {
   const RecLayout L = rec_layout(K, A, S);
-  return (size_t)((L.n2 + 3) & ~3) + 12 * (8 * NT + 7) + (64 * NT + 16) + (64 * NT + 4) + 32;
+  return (size_t)((L.n2 + 3) & ~3) + 12 * (8 * NT + 7) + (64 * NT + 16) + (64 * NT + 4) + 128;
 }
 __device__ inline TileSmem carve_tile(double* q, const RecLayout& L, int NT) {
   TileSmem w;
@@ -162,7 +162,7 @@ __device__ inline void tile_phase1(const KModel& m, const RecLayout& L, double* 
     if (fast) {
       h = 1.0 / scale;
       xT = (double)T * h;
-      if (!(h <= 3.6) || !(xT >= 3.0)) fast = false;
+      if (!(h <= 48.0) || !(xT >= 3.0)) fast = false;
     }
     if (fast) {
       const double kmed = fmax(alph - 1.0 / 3.0, 0.0) * scale;
@@ -231,32 +231,35 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
   double* ctab = w.ctab;
   const double kLogTol = 41.5;
 
+  // number of interval-mass coefficients: the scaled coefficients c'_m = c_m / x_{km+1}^m decay like P(m+1, h)
+  const int nct = (h <= 3.6) ? 32 : (h <= 16.0) ? 64 : (h <= 32.0) ? 96 : 128;
   if (fast && km < T) {
-    // interval-mass table: lane mm holds c_mm = binom(a-1, mm) * gamma(mm+1, h)
-    const int mm = lane;
-    double term = m.rk[mm + 1], sum = term;
-    int j = 1;
-    while (__any_sync(0xffffffffu, term > 1e-18 * sum) && j < 120) {
-      term *= h * m.rk[mm + 1 + j];
-      sum += term;
-      j++;
-    }
-    double hp = h, bn = (mm >= 1) ? (alph - (double)mm) * m.rk[mm] : 1.0;
+    // c'_m = binom(a-1, m) (km+1)^-m * h e^-h sigma_m,  sigma_m = sum_j h^j / ((m+1)...(m+1+j));  lane holds m = lane + 32 g
+    const double emh = exp(-h), rk1 = m.rk[km + 1];
+    double carry = 1.0, c0 = 0.0, clast = 0.0;
+    for (int g = 0; g < (nct >> 5); g++) {
+      const int mm = lane + 32 * g;
+      double term = m.rk[mm + 1], sum = term;
+      int j = 1;
+      while (__any_sync(0xffffffffu, term > 1e-18 * sum) && j < 400) {
+        term *= h * m.rk[mm + 1 + j];
+        sum += term;
+        j++;
+      }
+      double bn = (mm >= 1) ? (alph - (double)mm) * m.rk[mm] * rk1 : 1.0;  // inclusive prefix product -> binom(a-1, m) (km+1)^-m
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double t1 = __shfl_up_sync(0xffffffffu, hp, o), t2 = __shfl_up_sync(0xffffffffu, bn, o);
-      if (lane >= o) { hp *= t1; bn *= t2; }
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t1 = __shfl_up_sync(0xffffffffu, bn, o);
+        if (lane >= o) bn *= t1;
+      }
+      bn *= carry;
+      carry = __shfl_sync(0xffffffffu, bn, 31);
+      const double cm = bn * (h * emh * sum);
+      ctab[mm] = cm;
+      if (g == 0) c0 = __shfl_sync(0xffffffffu, cm, 0);
+      clast = __shfl_sync(0xffffffffu, cm, 31);
     }
-    const double emh = exp(-h);
-    double cm = bn * (emh * hp * sum);
-    if (mm == 0) cm = 1.0 - emh;  // gamma(1, h); h is O(0.05..3.6), no cancellation worth an expm1
-    ctab[mm] = cm;
-    const double u1 = scale * m.rk[km + 1];
-    double pw = u1;
-#pragma unroll
-    for (int q = 0; q < 5; q++) pw *= pw;
-    const double c31 = __shfl_sync(0xffffffffu, cm, 31), c0 = __shfl_sync(0xffffffffu, cm, 0);
-    if (!(fabs(c31) * pw <= 1e-18 * c0 * fmin(u1, 1.0)) || !(u1 < 4.0)) fast = false;
+    if (!(fabs(clast) <= 1e-18 * c0)) fast = false;  // table not converged at the first upper day
   }
   if (!fast) {
     // general algorithm (R's pgamma_raw region split), one day per lane and round
@@ -271,24 +274,35 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
     }
   } else {
     for (int n = lane; n <= nser; n += 32) tab[n] = 1.0 / (alph + (double)n);
-    // series lengths of the upper rounds, one per lane: M_r = 2 + 41.5 / log(k0_r / A)
+    // upper part: interval masses for k = km+1 .. T-1, written to P[k]; two days per lane and round.
+    // I(x_k) = sum_m c'_m v^m with v = (km+1)/k; terms beyond M are below e^-41.5 of the leading one ((A/k)^m decay)
     const double A = fmax(1.0, fabs(alph - 1.0));
-    int Mr = 32;
-    {
-      const int k0 = km + 1 + 32 * lane;
-      if (k0 < T && (double)k0 > 1.5 * A) Mr = min(32, 2 + (int)(kLogTol / (m.logk[k0] - log(A))));
-    }
+    const double k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;             // masses beyond are < 2^-54 of the total: 0
+    const int kend = (k_hi >= (double)T) ? T : min(T, (int)k_hi + 2);
+    const double kp1 = (double)(km + 1), logA = log(A);
     __syncwarp();
-    // upper part: interval masses, k = km+1 .. T-1, written to P[k]
-    for (int k0 = km + 1, r = 0; k0 < T; k0 += 32, r++) {
-      const int k = k0 + lane;
-      const int M = __shfl_sync(0xffffffffu, Mr, r & 31);
-      const int kc = min(k, T);
-      const double u = scale * m.rk[kc];
-      double I = ctab[M - 1];
-      for (int q = M - 2; q >= 0; q--) I = fma(I, u, ctab[q]);
-      const double f = exp((alph - 1.0) * (m.logk[kc] - lsc) - (double)k * h - lgam_a);
-      if (k < T) P[k] = f * I;
+    for (int k0 = km + 1; k0 < T; k0 += 64) {
+      const int ka = k0 + lane, kb = ka + 32;
+      if (k0 >= kend) {
+        if (ka < T) P[ka] = 0.0;
+        if (kb < T) P[kb] = 0.0;
+        continue;
+      }
+      int M = nct;
+      if ((double)k0 > 1.5 * A) M = min(nct, 2 + (int)(kLogTol / (m.logk[k0] - logA)));
+      const int kac = min(ka, T), kbc = min(kb, T);
+      const double va = kp1 * m.rk[kac], vb = kp1 * m.rk[kbc];
+      double Ia = ctab[M - 1], Ib = Ia;
+      for (int q = M - 2; q >= 0; q--) {
+        const double cq = ctab[q];
+        Ia = fma(Ia, va, cq);
+        Ib = fma(Ib, vb, cq);
+      }
+      const double am1 = alph - 1.0;
+      const double fa = exp(am1 * (m.logk[kac] - lsc) - (double)ka * h - lgam_a);
+      const double fb = exp(am1 * (m.logk[kbc] - lsc) - (double)kb * h - lgam_a);
+      if (ka < T) P[ka] = fa * Ia;
+      if (kb < T) P[kb] = fb * Ib;
     }
     // lower part: series, days 1..km
     const double lgam_a1 = lgam_a + log(alph);
@@ -297,7 +311,20 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
       const double x = (double)k * h;
       double ssum = 1.0;
       for (int n = nser; n >= 1; n--) ssum = fma(x * tab[n], ssum, 1.0);
-      const double pv = exp(alph * (m.logk[min(k, T)] - lsc) - x - lgam_a1) * ssum;
+      const double lx = m.logk[min(k, T)] - lsc;
+      const double E = alph * lx - x - lgam_a1;
+      double pv;
+      if (E > -690.0 || !(alph > 1.0)) {
+        pv = exp(E) * ssum;
+      } else {
+        // Gradual-underflow regime: the reference forms P = pd_upper * dpois_wrap with dpois_wrap = exp(.) / sqrt(2 pi (a-1))
+        // (R nmath dpois_raw), and the subnormal exp(.) carries only a few bits.  Round at the same places so that the
+        // quantised value is the reference's (the operands agree to ~1e-12, the subnormal grid is ~1e-4 wide).
+        const double am1 = alph - 1.0;
+        const double t1 = exp(E - lx + log(alph) + 0.5 * log(CC_2PI * am1));  // = exp(-stirlerr(a-1) - bd0(a-1, x))
+        const double dd = t1 / sqrt(CC_2PI * am1);
+        pv = ((x / alph) * ssum) * dd;
+      }
       if (k <= km) P[k] = pv;
     }
     __syncwarp();
@@ -455,6 +482,8 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   }
   __syncwarp();
 
+  if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
+    for (int j = lane; j < T; j += 32) m.debug_dump[j] = w.gs[7 + j];
   // ---- S7 death-delay convolution on the tensor cores, then back to day order through shared memory
   {
     double auc[NT][2];
@@ -470,6 +499,13 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   }
   __syncwarp();
 
+  if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
+    for (int j = lane; j < T; j += 32) {
+      m.debug_dump[T + j] = w.xs[xs_index(j)];
+      m.debug_dump[2 * T + j] = w.gs[8 + j];
+      m.debug_dump[3 * T + j] = w.sk[min(j, m.M)];
+    }
+  }
   // ---- S8 Poisson term
   double l1 = 0.0, s_all = 0.0, s_unc = 0.0, dummy = 0.0;
   {

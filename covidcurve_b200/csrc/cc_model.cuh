@@ -28,6 +28,7 @@ struct KModel {
   double l2_prob[CC_MAX_STRATA];   // paobsd[a] / (running paobsd_sum), binomial.cpp:248-250 (data only)
   int sero_start[CC_MAX_SEROSURVEYS];
   int sero_end[CC_MAX_SEROSURVEYS];
+  double* debug_dump;              // developer aid: when non-null, vector 0 of a batch dumps dg[T], infxn[T], auc[T], CH[T] here
   int debug_stop;                  // developer switch (CC_DEBUG_STOP): stop the evaluation after stage n (0 = run everything)
   int gamma_mode;                  // 0: fast shared-shape evaluation with fallback, 1: always the general (R region-split) algorithm
   int jac_rows[3];
@@ -37,7 +38,7 @@ struct KModel {
   const double* pois_c;   // [T] -0.5*log(2*pi*x) - stirlerr(x) for x > 0, else 0   (x-only part of dpois)
   const double* lgx1;     // [T] lgamma(x+1)
   const double* logk;     // [T+1] log(k), k >= 1 (entry 0 unused): log of the integer days / lags
-  const double* rk;       // [max(T,160)+2] 1/k, k >= 1
+  const double* rk;       // [max(T,640)+2] 1/k, k >= 1
   double l1_const;        // sum of lgamma(x+1) over the days that enter L1 (uncensored, observed, x >= 0)
   const int* l3_kind;     // [S*A] 0: skipped (pos == n == -1), 1: regular counts, 2: irregular -> R's full dbinom case analysis
   const double* l3_lchoose;  // [S*A] lchoose(n, pos) for regular counts

@@ -52,11 +52,14 @@ extern "C" int cc_device_count(void) {
 constexpr int kEvalThreads = 128;
 
 constexpr int kWarpsPerCta = 4;
+#ifndef CC_MIN_CTAS
+#define CC_MIN_CTAS 4  // resident CTAs per SM the evaluation kernels are compiled for (caps registers at 128 per thread)
+#endif
 
 // Tile-phased evaluation (cc_eval_tile.cuh): each warp walks tiles of 32 consecutive parameter vectors.
 // theta is structure-of-arrays [d][ld]; scratch holds one record tile (F x 32 doubles) per warp of the grid.
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta) loglike_tile_kernel(const KModel m, const double* __restrict__ theta, long long n,
+__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_tile_kernel(const KModel m, const double* __restrict__ theta, long long n,
                                                                           long long ld, double* __restrict__ out, double* __restrict__ scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,7 +95,7 @@ __device__ __forceinline__ TileLane tile_lane(int le) {
 
 // initial state of every particle: phi, loglike, logprior
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_init_tile_kernel(const KModel m, const McmcState s, int le, double* __restrict__ scratch) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_init_tile_kernel(const KModel m, const McmcState s, int le, double* __restrict__ scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_init_tile_kernel(const
 // One sweep of d single-site Metropolis-Hastings updates for every (chain, rung); a warp owns E = 2^le particles.
 // `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_tile_kernel(const KModel m, const McmcState s, int iteration, int le,
+__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_sweep_tile_kernel(const KModel m, const McmcState s, int iteration, int le,
                                                                              double* __restrict__ scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -451,7 +454,11 @@ __global__ void dmma_probe_kernel(double* out, int iters, double a, double b) {
 
 // ------------------------------------------------------------------------------------------------ warp-kernel dispatch
 // NT = number of 64-day output tiles per evaluation; instantiated for the shapes in use (T <= 64 NT)
+#ifdef CC_NT_ONLY  // developer builds: instantiate a single tile count (faster compile)
+#define CC_FOR_EACH_NT(X) X(CC_NT_ONLY)
+#else
 #define CC_FOR_EACH_NT(X) X(4) X(5) X(7) X(16)
+#endif
 static int pick_nt(int T) {
   const int need = warp_tiles(T);
 #define CC_PICK(NT_) if (need <= NT_) return NT_;
@@ -558,6 +565,7 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
     k.gamma_mode = (gm && gm[0] == '1') ? 1 : 0;
     const char* ds = std::getenv("CC_DEBUG_STOP");
     k.debug_stop = ds ? std::atoi(ds) : 0;
+    k.debug_dump = nullptr;
   }
   k.serorev = de->account_serorev ? 1 : 0;
   k.binomial = de->binomial_likelihood ? 1 : 0;
@@ -610,7 +618,7 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   }
   std::vector<double> logk(T + 1, 0.0);
   for (int i = 1; i <= T; i++) logk[i] = std::log((double)i);
-  std::vector<double> rk(std::max(T, 160) + 2, 0.0);
+  std::vector<double> rk(std::max(T, 640) + 2, 0.0);
   for (size_t i = 1; i < rk.size(); i++) rk[i] = 1.0 / (double)i;
   {
     long double c = 0.0L;
@@ -677,8 +685,23 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
     cc_model_destroy(m);
     return fail(CC_E_CUDA, std::string("cc_model_create: ") + cudaGetErrorString(e));
   }
+  if (std::getenv("CC_DEBUG_DUMP")) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)4 * T * sizeof(double)) == cudaSuccess) {
+      cudaMemset(p, 0, (size_t)4 * T * sizeof(double));
+      m->dev_allocs.push_back(p);
+      m->k.debug_dump = static_cast<double*>(p);
+    }
+  }
   *out = m;
   return CC_OK;
+}
+
+// developer aid (not part of the public header): intermediates of vector 0 of the last batch; needs CC_DEBUG_DUMP=1 at model creation
+extern "C" int cc_debug_fetch(cc_model* m, double* out4T) {
+  if (!m || !m->k.debug_dump || !out4T) return CC_E_INVALID;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out4T, m->k.debug_dump, (size_t)4 * m->k.T * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess ? CC_OK : CC_E_CUDA;
 }
 
 extern "C" void cc_model_destroy(cc_model* m) {

@@ -29,7 +29,7 @@ for l in dis[start + 1:]:
         chain.append((m.group(1), int(m.group(2))))
         mine = [c for c in chain if ours(c[0])]
         if os.environ.get("NCU_LINES_OUTER"):  # attribute to the line of the top-level evaluation function (stage view)
-            body = [c for c in chain if c[0].endswith("cc_eval_warp.cuh")]
+            body = [c for c in chain if c[0].endswith("cc_eval_tile.cuh")]
             cur = body[-1] if body else chain[-1]
         else:
             cur = mine[0] if mine else chain[-1]
@@ -37,7 +37,7 @@ for l in dis[start + 1:]:
     if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
         lines.append(cur)
         fresh = True
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ("loglike_warp" if "loglike" in kern else "mcmc_sweep")],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ("loglike_tile" if "loglike" in kern else "mcmc_sweep")],
                      capture_output=True, text=True).stdout.splitlines()
 rows = list(csv.reader(out))
 hi = next(i for i, r in enumerate(rows) if "# Samples" in r)
