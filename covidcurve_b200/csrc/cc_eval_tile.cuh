@@ -280,6 +280,11 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
     const double k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;             // masses beyond are < 2^-54 of the total: 0
     const int kend = (k_hi >= (double)T) ? T : min(T, (int)k_hi + 2);
     const double kp1 = (double)(km + 1), logA = log(A);
+    int Mr = nct;  // series length of round `lane` (64 days per round)
+    {
+      const int k0 = km + 1 + 64 * lane;
+      if (k0 < T && (double)k0 > 1.5 * A) Mr = min(nct, 2 + (int)(kLogTol / (m.logk[k0] - logA)));
+    }
     __syncwarp();
     for (int k0 = km + 1; k0 < T; k0 += 64) {
       const int ka = k0 + lane, kb = ka + 32;
@@ -288,8 +293,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
         if (kb < T) P[kb] = 0.0;
         continue;
       }
-      int M = nct;
-      if ((double)k0 > 1.5 * A) M = min(nct, 2 + (int)(kLogTol / (m.logk[k0] - logA)));
+      const int M = __shfl_sync(0xffffffffu, Mr, (k0 - km - 1) >> 6);
       const int kac = min(ka, T), kbc = min(kb, T);
       const double va = kp1 * m.rk[kac], vb = kp1 * m.rk[kbc];
       double Ia = ctab[M - 1], Ib = Ia;
@@ -321,7 +325,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
         // (R nmath dpois_raw), and the subnormal exp(.) carries only a few bits.  Round at the same places so that the
         // quantised value is the reference's (the operands agree to ~1e-12, the subnormal grid is ~1e-4 wide).
         const double am1 = alph - 1.0;
-        const double t1 = exp(E - lx + log(alph) + 0.5 * log(CC_2PI * am1));  // = exp(-stirlerr(a-1) - bd0(a-1, x))
+        const double t1 = exp_gradual(E - lx + log(alph) + 0.5 * log(CC_2PI * am1));  // = exp(-stirlerr(a-1) - bd0(a-1, x))
         const double dd = t1 / sqrt(CC_2PI * am1);
         pv = ((x / alph) * ssum) * dd;
       }
@@ -457,15 +461,19 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   double tot = 0.0;
   {
     const int K = m.K;
+    // interval thresholds in registers (the common K = 5 has three); longer knot vectors fall back to shared memory
+    const double cd0 = (K > 2) ? w.rec[L.cday] : 1e300, cd1 = (K > 3) ? w.rec[L.cday + 1] : 1e300, cd2 = (K > 4) ? w.rec[L.cday + 2] : 1e300;
+    const double y0 = w.rec[L.spl + 1];
+#pragma unroll 2
     for (int i = lane; i < 64 * NT; i += 32) {
       double v = 0.0;
       if (i < T) {
-        int j = 0;
         const double di = (double)i;
-        for (int mI = 0; mI < K - 2; mI++) j += (w.rec[L.cday + mI] < di) ? 1 : 0;
+        int j = ((cd0 < di) ? 1 : 0) + ((cd1 < di) ? 1 : 0) + ((cd2 < di) ? 1 : 0);
+        for (int mI = 3; mI < K - 2; mI++) j += (w.rec[L.cday + mI] < di) ? 1 : 0;
         const double* c = w.rec + L.spl + 5 * j;
         const double dx = (double)(i + 1) - c[0];
-        const double y = (i == 0) ? w.rec[L.spl + 1] : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
+        const double y = (i == 0) ? y0 : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
         v = exp(y);
         tot += v;
       }
@@ -511,6 +519,7 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   {
     const double snm = w.rec[L.snm];
     const double* aucs = w.gs + 8;
+#pragma unroll 2
     for (int j = lane; j < T; j += 32) {
       const double a = aucs[j];
       const double expd = a * snm;
@@ -540,6 +549,7 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   for (int s = 0; s < S; s++) {
     const int st = m.sero_start[s], en = m.sero_end[s];
     double b = 0.0;
+#pragma unroll 2
     for (int t = lane; t < en; t += 32) {
       int lo = st - 1 - t;
       lo = lo < 0 ? 0 : lo;

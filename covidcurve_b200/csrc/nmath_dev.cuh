@@ -207,13 +207,22 @@ __device__ __forceinline__ GammaShape gamma_shape(double alph) {
   return g;
 }
 
+// exp(x) whose SUBNORMAL results are rounded once, to the subnormal grid (like a correctly rounded libm exp): the value is
+// formed in the normal range and scaled by an exact power of two.  Matters only below ~1e-308, where the reference's
+// gamma-cdf values carry a handful of bits and every rounding shows in the log-likelihood.
+__device__ __forceinline__ double exp_gradual(double x) {
+  if (x > -700.0) return exp(x);
+  return ldexp(exp(x + 200.0 * CC_LN2), -200);
+}
+
 // dpois_raw(k, lambda) with k in {alph-1, alph}: Loader form with the k-only terms taken from GammaShape
 __device__ __forceinline__ double dpois_shape(double k, double stir_k, double rs2pi_k, double lambda) {
   if (lambda == 0) return (k == 0) ? 1.0 : 0.0;
   if (!isfinite(lambda)) return 0.0;
   if (k <= lambda * DBL_MIN) return exp(-lambda);
   if (lambda < k * DBL_MIN) return exp(-lambda + k * log(lambda) - lgamma(k + 1));
-  return exp(-stir_k - bd0(k, lambda)) * rs2pi_k;
+  (void)rs2pi_k;
+  return exp_gradual(-stir_k - bd0(k, lambda)) / sqrt(CC_2PI * k);  // R_D_fexp(2 pi k, .): same rounding points as R
 }
 
 // dpois_wrap(alph, x) = dpois(alph-1, x)

@@ -1,0 +1,110 @@
+"""GPU-resident Metropolis-coupled MCMC against the CPU restatement with the SAME counter-based random numbers: the two
+runs must make the same accept/reject and swap decisions, so whole trajectories agree to rounding."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(spec, **kw):
+    from covidcurve_b200 import _lib
+    from oracle.oracle import Oracle
+    model = _lib.Model(spec, device=0)
+    mc = _lib.Mcmc(model, record_rungs=True, **kw)
+    mc.advance(kw["burnin"] + kw["samples"] - 1)
+    got, diag = mc.fetch(), mc.diagnostics()
+    o_kw = {k: v for k, v in kw.items() if k not in ("chain_offset",)}
+    want = Oracle(spec).mcmc(nthreads=4, chain_offset=kw.get("chain_offset", 0), **o_kw)
+    return got, diag, want, mc
+
+
+def test_trajectory_parity_single_rung(built_lib, modfit):
+    spec, _ = modfit
+    got, diag, want, mc = _run_both(spec, burnin=120, samples=80, rungs=1, chains=3, seed=21)
+    assert got["theta"].shape == want["theta"].shape == (3, 1, 200, spec.d)
+    np.testing.assert_allclose(got["theta"], want["theta"], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(got["loglike"], want["loglike"], rtol=1e-9)
+    np.testing.assert_allclose(got["logprior"], want["logprior"], rtol=1e-9)
+    assert list(got["iteration"]) == list(range(1, 201))
+    assert mc.loglike_evals == 3 * (1 + 199 * spec.d)
+
+
+def test_trajectory_parity_tempered_with_swaps(built_lib, modfit):
+    spec, _ = modfit
+    got, diag, want, _ = _run_both(spec, burnin=60, samples=60, rungs=5, chains=2, seed=4, GTI_pow=3.0)
+    np.testing.assert_allclose(diag["beta"], want["beta"])
+    np.testing.assert_allclose(got["theta"], want["theta"], rtol=1e-9)
+    np.testing.assert_allclose(got["loglike"], want["loglike"], rtol=1e-9)
+    np.testing.assert_allclose(diag["mc_accept"], want["mc_accept"], rtol=1e-12)
+
+
+def test_trajectory_parity_logit_serorev_reparam(built_lib):
+    from covidcurve_b200 import synth
+    spec, _ = synth.make_spec("cfg2", reparam=True)
+    got, diag, want, _ = _run_both(spec, burnin=25, samples=15, rungs=3, chains=2, seed=9)
+    np.testing.assert_allclose(got["theta"], want["theta"], rtol=1e-9)
+    np.testing.assert_allclose(got["loglike"], want["loglike"], rtol=1e-9)
+
+
+def test_sharding_is_invisible(built_lib, modfit):
+    """Chains [0, 4) in one handle == chains [0, 2) and [2, 4) in two handles (what two GPUs would run)."""
+    from covidcurve_b200 import _lib
+    spec, _ = modfit
+    model = _lib.Model(spec, device=0)
+    kw = dict(burnin=40, samples=20, rungs=3, seed=77)
+    whole = _lib.Mcmc(model, chains=4, **kw); whole.advance(59)
+    a = _lib.Mcmc(model, chains=2, chain_offset=0, **kw); a.advance(59)
+    b = _lib.Mcmc(model, chains=2, chain_offset=2, **kw); b.advance(59)
+    w, fa, fb = whole.fetch(), a.fetch(), b.fetch()
+    assert np.array_equal(w["theta"][:2], fa["theta"]) and np.array_equal(w["theta"][2:], fb["theta"])
+    assert np.array_equal(w["loglike"][2:], fb["loglike"])
+
+
+def test_cold_rung_only_recording_and_thinning(built_lib, modfit):
+    from covidcurve_b200 import _lib
+    spec, _ = modfit
+    model = _lib.Model(spec, device=0)
+    full = _lib.Mcmc(model, burnin=30, samples=30, rungs=3, chains=2, seed=5, record_rungs=True); full.advance(59)
+    cold = _lib.Mcmc(model, burnin=30, samples=30, rungs=3, chains=2, seed=5, record_rungs=False, thin=4); cold.advance(59)
+    f, c = full.fetch(), cold.fetch()
+    keep = np.arange(4, 61, 4)                       # main.R:196-202: iteration %in% seq(thinning, burnin+samples, thinning)
+    assert list(c["iteration"]) == list(keep)
+    assert np.array_equal(c["theta"][:, 0], f["theta"][:, 2][:, keep - 1])   # cold rung = last rung position
+
+
+def test_run_IFRmodel_age_api_shapes(built_lib, modfit):
+    """The host-side mirror of run_IFRmodel_age returns the drjacoby_output field list."""
+    import pandas as pd
+    from covidcurve_b200 import api
+    spec, g = modfit
+    A, S = spec.A, spec.S
+    mdl = api.make_IFRmodel_age.new()
+    mdl.set_MeanTODparam("mod"); mdl.set_CoefVarOnsetTODparam("sod")
+    mdl.set_IFRparams(spec.IFRparams); mdl.set_maxMa("ma3")
+    mdl.set_Knotparams(spec.Knotparams); mdl.set_relKnot("x4")
+    mdl.set_Infxnparams(spec.Infxnparams); mdl.set_relInfxn("y5")
+    mdl.set_Noiseparams(spec.Noiseparams)
+    mdl.set_Serotestparams(["sens", "spec", "sero_con_rate"])
+    sero = pd.DataFrame({"SeroStartSurvey": np.repeat(spec.sero_survey_start, A), "SeroEndSurvey": np.repeat(spec.sero_survey_end, A),
+                         "Strata": spec.IFRparams * S, "SeroPos": spec.sero_a, "SeroN": spec.sero_b,
+                         "SeroPrev": spec.sero_a / spec.sero_b, "SeroLCI": np.nan, "SeroUCI": np.nan})
+    mdl.set_data({"obs_deaths": pd.DataFrame({"ObsDay": np.arange(1, spec.T + 1), "Deaths": spec.obs_deaths}),
+                  "prop_deaths": pd.DataFrame({"Strata": spec.IFRparams, "PropDeaths": spec.prop_strata_obs_deaths}),
+                  "obs_serology": sero})
+    mdl.set_demog(pd.DataFrame({"Strata": spec.IFRparams, "popN": spec.demog}))
+    mdl.set_paramdf(pd.DataFrame({"name": spec.names, "min": spec.pmin, "init": spec.pinit, "max": spec.pmax,
+                                  "dsc1": spec.dsc1, "dsc2": spec.dsc2}))
+    fit = api.run_IFRmodel_age(mdl, reparamIFR=False, reparamInfxn=False, reparamKnots=False, burnin=40, samples=40, rungs=2,
+                               chains=2, seed=3)
+    out = fit["mcmcout"]["output"]
+    assert list(out.columns[:6]) == ["chain", "rung", "iteration", "stage", "logprior", "loglikelihood"]
+    assert list(out.columns[6:]) == spec.names
+    assert len(out) == 2 * 2 * 80 and set(out["stage"]) == {"burnin", "sampling"}
+    first = out[(out["chain"] == "chain1") & (out["rung"] == "rung2") & (out["iteration"] == 1)]
+    assert first["loglikelihood"].iloc[0] == pytest.approx(-231967.69462831024, rel=1e-12)   # row 1 = init (stored fit)
+    assert set(fit["mcmcout"]["diagnostics"]) >= {"rhat", "rung_details", "mc_accept"}
+    assert list(fit["mcmcout"]["parameters"]) == ["data", "df_params", "loglike", "logprior", "burnin", "samples", "rungs", "chains",
+                                                  "coupling_on", "GTI_pow", "beta_manual"]
+    from covidcurve_b200 import summaries
+    ci = summaries.get_cred_intervals(fit, "IFRparams", by_chain=False)
+    assert list(ci["param"]) == spec.IFRparams and np.all(ci["LCI"] <= ci["UCI"])
