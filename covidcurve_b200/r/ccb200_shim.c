@@ -1,0 +1,190 @@
+/*
+ * ccb200_shim.c - the .Call layer an R installation of COVIDCurve adds to reach libcovidcurve_b200.so.
+ *
+ * NOT compiled in this repository's build (R and its headers are absent from the build image):
+ * it is the thin binding a maintainer drops into COVIDCurve/src/ next to RcppExports.cpp.  Every entry point only
+ * unpacks R vectors into the plain-pointer C ABI of include/covidcurve_b200.h; no logic lives here.
+ *
+ * Replaces, on the R side:
+ *   .Call("_COVIDCurve_natcubspline_loglike_binomial" | "..._logit", params, param_i, data, misc)   src/RcppExports.cpp:10-35
+ *   drjacoby::run_mcmc(data, df_params, misc, loglike, logprior, ...)                               R/main.R:179-193
+ *
+ * Build inside the R package:  PKG_CPPFLAGS = -I<repo>/include   PKG_LIBS = -L<repo>/covidcurve_b200 -lcovidcurve_b200
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "covidcurve_b200.h"
+
+static void ccb_fail(const char* where) { Rf_error("%s: %s", where, cc_last_error()); }
+
+static SEXP list_get(SEXP lst, const char* name) {
+  SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  for (R_xlen_t i = 0; i < XLENGTH(lst); i++)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(lst, i);
+  Rf_error("missing element '%s'", name);
+  return R_NilValue;
+}
+static int as_int(SEXP x) { return Rf_asInteger(x); }
+
+static void model_finalizer(SEXP ptr) {
+  cc_model* m = (cc_model*)R_ExternalPtrAddr(ptr);
+  if (m) cc_model_destroy(m);
+  R_ClearExternalPtr(ptr);
+}
+
+/*
+ * CCB_model_create(desc): `desc` is a named list built by R/ccb200.R from exactly the objects run_IFRmodel_age already
+ * builds - data_list (R/main.R:136-152), misc_list (:158-166), IFRmodel$paramdf (:172) - plus the role map and prior
+ * table that R/Agecpp2strings.R otherwise bakes into C++ source strings.  Integer vectors are 0-based row indices.
+ */
+SEXP CCB_model_create(SEXP desc, SEXP device) {
+  cc_model_desc d;
+  memset(&d, 0, sizeof d);
+  d.abi_version = CC_ABI_VERSION;
+  d.n_params = as_int(list_get(desc, "n_params"));
+  d.n_strata = as_int(list_get(desc, "n_strata"));
+  d.n_knots = as_int(list_get(desc, "n_knots"));
+  d.days_obsd = as_int(list_get(desc, "days_obsd"));
+  d.n_sero_obs = as_int(list_get(desc, "n_sero_obs"));
+  d.max_seroday_obsd = as_int(list_get(desc, "max_seroday_obsd"));
+  d.rcensor_day = as_int(list_get(desc, "rcensor_day"));
+  d.account_serorev = as_int(list_get(desc, "account_serorev"));
+  d.binomial_likelihood = as_int(list_get(desc, "binomial_likelihood"));
+  d.reparam_ifr = as_int(list_get(desc, "reparam_ifr"));
+  d.reparam_knots = as_int(list_get(desc, "reparam_knots"));
+  d.reparam_infxn = as_int(list_get(desc, "reparam_infxn"));
+  d.demog = REAL(list_get(desc, "demog"));
+  d.obs_deaths = REAL(list_get(desc, "obs_deaths"));
+  d.prop_strata_obs_deaths = REAL(list_get(desc, "prop_strata_obs_deaths"));
+  d.sero_a = REAL(list_get(desc, "sero_a"));
+  d.sero_b = REAL(list_get(desc, "sero_b"));
+  d.sero_survey_start = INTEGER(list_get(desc, "sero_survey_start"));
+  d.sero_survey_end = INTEGER(list_get(desc, "sero_survey_end"));
+  d.idx_sens = as_int(list_get(desc, "idx_sens"));
+  d.idx_spec = as_int(list_get(desc, "idx_spec"));
+  d.idx_sero_con_rate = as_int(list_get(desc, "idx_sero_con_rate"));
+  d.idx_sero_rev_shape = as_int(list_get(desc, "idx_sero_rev_shape"));
+  d.idx_sero_rev_scale = as_int(list_get(desc, "idx_sero_rev_scale"));
+  d.idx_mod = as_int(list_get(desc, "idx_mod"));
+  d.idx_sod = as_int(list_get(desc, "idx_sod"));
+  d.idx_knots = INTEGER(list_get(desc, "idx_knots"));
+  d.idx_infxn = INTEGER(list_get(desc, "idx_infxn"));
+  d.idx_ifr = INTEGER(list_get(desc, "idx_ifr"));
+  d.idx_noise = INTEGER(list_get(desc, "idx_noise"));
+  d.idx_rel_knot = as_int(list_get(desc, "idx_rel_knot"));
+  d.idx_rel_infxn = as_int(list_get(desc, "idx_rel_infxn"));
+  d.idx_max_ma = as_int(list_get(desc, "idx_max_ma"));
+  d.pmin = REAL(list_get(desc, "pmin"));
+  d.pmax = REAL(list_get(desc, "pmax"));
+  d.prior_family = INTEGER(list_get(desc, "prior_family"));
+  d.prior_p1 = REAL(list_get(desc, "prior_p1"));
+  d.prior_p2 = REAL(list_get(desc, "prior_p2"));
+  SEXP jr = list_get(desc, "jac_rows"), jc = list_get(desc, "jac_counts");
+  for (int j = 0; j < 3; j++) {
+    d.jac_rows[j] = INTEGER(jr)[j];
+    d.jac_counts[j] = REAL(jc)[j];
+  }
+  cc_model* m = NULL;
+  if (cc_model_create(&d, as_int(device), &m) != CC_OK) ccb_fail("cc_model_create");
+  SEXP ptr = PROTECT(R_MakeExternalPtr(m, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, model_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+/* scalar drop-ins for COVIDCurve:::natcubspline_loglike_binomial/_logit (R/RcppExports.R:4-10): list(LogLik = ) */
+SEXP CCB_loglike(SEXP model, SEXP params, SEXP param_i) {
+  cc_model* m = (cc_model*)R_ExternalPtrAddr(model);
+  double out = NA_REAL;
+  if (cc_loglike(m, REAL(params), as_int(param_i), &out) != CC_OK) ccb_fail("cc_loglike");
+  SEXP ret = PROTECT(Rf_allocVector(VECSXP, 1)), nm = PROTECT(Rf_allocVector(STRSXP, 1));
+  SET_VECTOR_ELT(ret, 0, Rf_ScalarReal(out));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("LogLik"));
+  Rf_setAttrib(ret, R_NamesSymbol, nm);
+  UNPROTECT(2);
+  return ret;
+}
+
+/* batched evaluation: theta is an n x d numeric matrix (one parameter vector per ROW, columns in df_params order); R's
+   column-major storage is exactly the structure-of-arrays [d][n] layout of cc_loglike_batch, so no copy is made */
+SEXP CCB_loglike_batch(SEXP model, SEXP theta) {
+  cc_model* m = (cc_model*)R_ExternalPtrAddr(model);
+  const int64_t n = Rf_nrows(theta);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+  if (cc_loglike_batch(m, REAL(theta), n, n, REAL(out), CC_MEM_HOST, NULL) != CC_OK) ccb_fail("cc_loglike_batch");
+  UNPROTECT(1);
+  return out;
+}
+SEXP CCB_logprior_batch(SEXP model, SEXP theta) {
+  cc_model* m = (cc_model*)R_ExternalPtrAddr(model);
+  const int64_t n = Rf_nrows(theta);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+  if (cc_logprior_batch(m, REAL(theta), n, n, REAL(out), CC_MEM_HOST, NULL) != CC_OK) ccb_fail("cc_logprior_batch");
+  UNPROTECT(1);
+  return out;
+}
+
+/*
+ * CCB_mcmc_run(model, opts): the replacement of drjacoby::run_mcmc at R/main.R:179.  Returns a list
+ *   theta [rows x d x rungs x chains] (R array), loglikelihood / logprior [rows x rungs x chains], iteration [rows],
+ *   beta [rungs], mc_accept [(rungs-1) x chains]
+ * which R/ccb200.R reshapes into the `drjacoby_output` data frame (chain, rung, iteration, stage, logprior, loglikelihood, ...).
+ */
+SEXP CCB_mcmc_run(SEXP model, SEXP opts) {
+  cc_model* m = (cc_model*)R_ExternalPtrAddr(model);
+  cc_mcmc_opts o;
+  memset(&o, 0, sizeof o);
+  o.burnin = as_int(list_get(opts, "burnin"));
+  o.samples = as_int(list_get(opts, "samples"));
+  o.rungs = as_int(list_get(opts, "rungs"));
+  o.n_chains = as_int(list_get(opts, "chains"));
+  o.chain_offset = 0;
+  o.coupling_on = as_int(list_get(opts, "coupling_on"));
+  o.GTI_pow = Rf_asReal(list_get(opts, "GTI_pow"));
+  SEXP bm = list_get(opts, "beta_manual");
+  o.beta_manual = Rf_isNull(bm) ? NULL : REAL(bm);
+  o.seed = (uint64_t)Rf_asReal(list_get(opts, "seed"));
+  o.cold_rung_last = 1;
+  o.record_rungs = 1;
+  o.thin = 1;
+  o.init = NULL;
+  o.init_default = REAL(list_get(opts, "init"));
+  cc_mcmc* s = NULL;
+  if (cc_mcmc_create(m, &o, &s) != CC_OK) ccb_fail("cc_mcmc_create");
+  if (cc_mcmc_advance(s, o.burnin + o.samples - 1) != CC_OK) { cc_mcmc_destroy(s); ccb_fail("cc_mcmc_advance"); }
+  const R_xlen_t rows = (R_xlen_t)cc_mcmc_rows(s), d = Rf_length(list_get(opts, "init")), R = o.rungs, C = o.n_chains;
+  SEXP theta = PROTECT(Rf_allocVector(REALSXP, rows * d * R * C)), ll = PROTECT(Rf_allocVector(REALSXP, rows * R * C)),
+       lp = PROTECT(Rf_allocVector(REALSXP, rows * R * C)), it = PROTECT(Rf_allocVector(INTSXP, rows)),
+       beta = PROTECT(Rf_allocVector(REALSXP, R)), acc = PROTECT(Rf_allocVector(REALSXP, (R > 1 ? R - 1 : 1) * C));
+  /* the C layout [chain][rung][row][d] read as column-major is a d x rows x rungs x chains array */
+  if (cc_mcmc_fetch(s, REAL(theta), REAL(ll), REAL(lp), INTEGER(it)) != CC_OK ||
+      cc_mcmc_diagnostics(s, REAL(beta), REAL(acc), NULL, NULL) != CC_OK) {
+    cc_mcmc_destroy(s);
+    ccb_fail("cc_mcmc_fetch");
+  }
+  cc_mcmc_destroy(s);
+  const char* nms[] = {"theta", "loglikelihood", "logprior", "iteration", "beta", "mc_accept"};
+  SEXP vals[] = {theta, ll, lp, it, beta, acc};
+  SEXP ret = PROTECT(Rf_allocVector(VECSXP, 6)), nm = PROTECT(Rf_allocVector(STRSXP, 6));
+  for (int i = 0; i < 6; i++) {
+    SET_VECTOR_ELT(ret, i, vals[i]);
+    SET_STRING_ELT(nm, i, Rf_mkChar(nms[i]));
+  }
+  Rf_setAttrib(ret, R_NamesSymbol, nm);
+  UNPROTECT(8);
+  return ret;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"CCB_model_create", (DL_FUNC)&CCB_model_create, 2},   {"CCB_loglike", (DL_FUNC)&CCB_loglike, 3},
+    {"CCB_loglike_batch", (DL_FUNC)&CCB_loglike_batch, 2}, {"CCB_logprior_batch", (DL_FUNC)&CCB_logprior_batch, 2},
+    {"CCB_mcmc_run", (DL_FUNC)&CCB_mcmc_run, 2},           {NULL, NULL, 0}};
+
+void R_init_ccb200(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
