@@ -287,7 +287,7 @@ def main():
         alg_bytes = (8 * d + 8) * V
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-            "kernel": "loglike_warp_kernel", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
+            "kernel": "loglike_tile_kernel", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
             "peak_source": "max of cc_fp64_peak_probe (register-resident DFMA chains: %.2f) and cc_dmma_probe (mma.sync m8n8k4 f64: %.2f), measured "
                            "live in this run; MEASURED_PEAKS.json has no FP64 entry" % (dfma_tf, dmma_tf),
             "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
