@@ -296,7 +296,7 @@ class Mcmc:
         return dict(beta=beta, mc_accept=mc, move_accept=mv, bw=bw.reshape(self.chains, self.rungs, self.d))
 
 
-FN = dict(pgamma=1, dpois=2, dbinom=3, dnorm=4, dbeta=5, dunif=6, pweibull=7, stirlerr=8, bd0=9)
+FN = dict(pgamma=1, dpois=2, dbinom=3, dnorm=4, dbeta=5, dunif=6, pweibull=7, stirlerr=8, bd0=9, fastlog=10)
 
 
 def nmath(fn: str, a, b=0.0, c=0.0, device: int = 0):

@@ -43,6 +43,21 @@ __host__ __device__ inline RecLayout rec_layout(int K, int A, int S) {
   return L;
 }
 
+// read-only per-day tables.  Staging them in shared memory per CTA was measured SLOWER than leaving them in global memory
+// (they are a few kB and stay L1 resident; the extra 6 kB of shared memory per CTA shrinks the L1): 58 vs 65 M evals/s.
+struct TileTables {
+  const double* logk;  // [T+1]
+  const double* rk;    // [nrk]
+  const int* obsd;     // [T]
+  int nrk;
+};
+__host__ __device__ inline size_t tile_tables_doubles(int) { return 0; }
+__device__ inline TileTables tile_tables_load(const KModel& m, double*) {
+  TileTables t;
+  t.logk = m.logk; t.rk = m.rk; t.obsd = m.obsd; t.nrk = 0x7fffffff;
+  return t;
+}
+
 struct TileSmem {
   double* rec;  // [n2 rounded] record of the vector being processed
   double* xs;   // padded series
@@ -220,7 +235,7 @@ __device__ inline void tile_phase1(const KModel& m, const RecLayout& L, double* 
 // ------------------------------------------------------------------------------------------------ phase 2 pieces
 // delay kernel: w.gs[7 + k] <- P(x_{k+1}) - P(x_k)
 template <int NT>
-__device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const TileSmem& w) {
+__device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb) {
   const int lane = threadIdx.x & 31, T = m.T;
   const double alph = w.rec[L.gam + 0], scale = w.rec[L.gam + 1], h = w.rec[L.gam + 2], lgam_a = w.rec[L.gam + 3],
                lsc = w.rec[L.gam + 4], QT = w.rec[L.gam + 7];
@@ -235,18 +250,18 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
   const int nct = (h <= 3.6) ? 32 : (h <= 16.0) ? 64 : (h <= 32.0) ? 96 : 128;
   if (fast && km < T) {
     // c'_m = binom(a-1, m) (km+1)^-m * h e^-h sigma_m,  sigma_m = sum_j h^j / ((m+1)...(m+1+j));  lane holds m = lane + 32 g
-    const double emh = exp(-h), rk1 = m.rk[km + 1];
+    const double emh = exp(-h), rk1 = tb.rk[km + 1];
     double carry = 1.0, c0 = 0.0, clast = 0.0;
     for (int g = 0; g < (nct >> 5); g++) {
       const int mm = lane + 32 * g;
-      double term = m.rk[mm + 1], sum = term;
+      double term = tb.rk[mm + 1], sum = term;
       int j = 1;
       while (__any_sync(0xffffffffu, term > 1e-18 * sum) && j < 400) {
-        term *= h * m.rk[mm + 1 + j];
+        term *= h * ((mm + 1 + j < tb.nrk) ? tb.rk[mm + 1 + j] : m.rk[mm + 1 + j]);
         sum += term;
         j++;
       }
-      double bn = (mm >= 1) ? (alph - (double)mm) * m.rk[mm] * rk1 : 1.0;  // inclusive prefix product -> binom(a-1, m) (km+1)^-m
+      double bn = (mm >= 1) ? (alph - (double)mm) * tb.rk[mm] * rk1 : 1.0;  // inclusive prefix product -> binom(a-1, m) (km+1)^-m
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const double t1 = __shfl_up_sync(0xffffffffu, bn, o);
@@ -283,7 +298,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
     int Mr = nct;  // series length of round `lane` (64 days per round)
     {
       const int k0 = km + 1 + 64 * lane;
-      if (k0 < T && (double)k0 > 1.5 * A) Mr = min(nct, 2 + (int)(kLogTol / (m.logk[k0] - logA)));
+      if (k0 < T && (double)k0 > 1.5 * A) Mr = min(nct, 2 + (int)(kLogTol / (tb.logk[k0] - logA)));
     }
     __syncwarp();
     for (int k0 = km + 1; k0 < T; k0 += 64) {
@@ -295,7 +310,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
       }
       const int M = __shfl_sync(0xffffffffu, Mr, (k0 - km - 1) >> 6);
       const int kac = min(ka, T), kbc = min(kb, T);
-      const double va = kp1 * m.rk[kac], vb = kp1 * m.rk[kbc];
+      const double va = kp1 * tb.rk[kac], vb = kp1 * tb.rk[kbc];
       double Ia = ctab[M - 1], Ib = Ia;
       for (int q = M - 2; q >= 0; q--) {
         const double cq = ctab[q];
@@ -303,8 +318,8 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
         Ib = fma(Ib, vb, cq);
       }
       const double am1 = alph - 1.0;
-      const double fa = exp(am1 * (m.logk[kac] - lsc) - (double)ka * h - lgam_a);
-      const double fb = exp(am1 * (m.logk[kbc] - lsc) - (double)kb * h - lgam_a);
+      const double fa = exp(am1 * (tb.logk[kac] - lsc) - (double)ka * h - lgam_a);
+      const double fb = exp(am1 * (tb.logk[kbc] - lsc) - (double)kb * h - lgam_a);
       if (ka < T) P[ka] = fa * Ia;
       if (kb < T) P[kb] = fb * Ib;
     }
@@ -315,7 +330,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
       const double x = (double)k * h;
       double ssum = 1.0;
       for (int n = nser; n >= 1; n--) ssum = fma(x * tab[n], ssum, 1.0);
-      const double lx = m.logk[min(k, T)] - lsc;
+      const double lx = tb.logk[min(k, T)] - lsc;
       const double E = alph * lx - x - lgam_a1;
       double pv;
       if (E > -690.0 || !(alph > 1.0)) {
@@ -373,7 +388,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
 
 // w.sk[k] <- CH[k] = sum_{u<k} H[u], k = 0..M  (binomial.cpp:257-284)
 template <int NT>
-__device__ inline void tile_sero_prefix(const KModel& m, const RecLayout& L, const TileSmem& w) {
+__device__ inline void tile_sero_prefix(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb) {
   const int lane = threadIdx.x & 31, M = m.M;
   const double rate = w.rec[L.sero];
   if (!m.serorev) {
@@ -393,7 +408,7 @@ __device__ inline void tile_sero_prefix(const KModel& m, const RecLayout& L, con
     double c = 0.0, sv = 0.0;
     if (k < M) {
       c = rr * exp(-(double)(k + 1) / rate);
-      sv = badw ? d_nan() : ((k == 0) ? 1.0 : exp(-exp(shape * (m.logk[k] - lws))));
+      sv = badw ? d_nan() : ((k == 0) ? 1.0 : exp(-exp(shape * (tb.logk[k] - lws))));
     }
     w.xs[xs_index(k)] = c;
     w.gs[7 + k] = sv;
@@ -447,15 +462,15 @@ __device__ __forceinline__ void warp_sum4(double& a, double& b, double& c, doubl
 
 // phase 2 for vector e of the tile: per-day stages; writes o_status, o_l1, o_texpd, o_sunc, o_base[S] to the scratch
 template <int NT>
-__device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, double* __restrict__ scr, int e) {
+__device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr, int e) {
   const int lane = threadIdx.x & 31, T = m.T, A = m.A, S = m.S;
   __syncwarp();
   for (int f = lane; f < L.n2; f += 32) w.rec[f] = scr[f * 32 + e];
   __syncwarp();
   if (w.rec[L.flags] == 0.0) return;  // knots not increasing: phase 3 returns the failure value
 
-  tile_sero_prefix<NT>(m, L, w);   // S10 (first: with seroreversion it borrows the series/kernel regions)
-  tile_gamma<NT>(m, L, w);         // S2
+  tile_sero_prefix<NT>(m, L, w, tb);   // S10 (first: with seroreversion it borrows the series/kernel regions)
+  tile_gamma<NT>(m, L, w, tb);         // S2
 
   // ---- S5 infection curve + S6 population check
   double tot = 0.0;
@@ -526,13 +541,13 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
       s_all += expd;
       if ((j + 1) < m.rcensor_day) {
         s_unc += a;
-        const int x = m.obsd[j];
+        const int x = tb.obsd[j];
         if (x != -1) {
           double lp;
           if (!(expd >= 0.0)) lp = d_nan();        // NaN or negative mean -> NaN (R::dpois)
           else if (x < 0) lp = -d_inf();
           else if (x == 0) lp = -expd;
-          else lp = (double)x * log(expd) - expd;  // - lgamma(x+1) is data only: m.l1_const
+          else lp = (double)x * fast_log(expd, m.logtab) - expd;  // - lgamma(x+1) is data only: m.l1_const
           l1 += lp;
         }
       }

@@ -86,8 +86,10 @@ __device__ __forceinline__ void toeplitz_dmma(const double* __restrict__ xs, con
   const int lane = threadIdx.x & 31, n = lane >> 2, t = lane & 3;
   const double* ap = gs + 7 + n - t;           // A[r = n][s = 4h + t] = g[8 delta + n - 4h - t]
   const double* bp = xs + kXsLead + 12 * n + t;  // B[s = 4h + t][col n] = x[8 (8P + n - delta) + 4h + t]
+  // two accumulator sets (one per k-half) keep twice as many independent MMA chains in flight; summed at the end
+  double acc1[NT][2];
 #pragma unroll
-  for (int P = 0; P < NT; P++) acc[P][0] = acc[P][1] = 0.0;
+  for (int P = 0; P < NT; P++) acc[P][0] = acc[P][1] = acc1[P][0] = acc1[P][1] = 0.0;
 #pragma unroll
   for (int D = 0; D < NT; D++) {
 #pragma unroll 2
@@ -103,10 +105,16 @@ __device__ __forceinline__ void toeplitz_dmma(const double* __restrict__ xs, con
         b1[P] = b[96 * P + 4];
       }
 #pragma unroll
-      for (int P = D; P < NT; P++) dmma884(acc[P][0], acc[P][1], a0, b0[P]);
-#pragma unroll
-      for (int P = D; P < NT; P++) dmma884(acc[P][0], acc[P][1], a1, b1[P]);
+      for (int P = D; P < NT; P++) {
+        dmma884(acc[P][0], acc[P][1], a0, b0[P]);
+        dmma884(acc1[P][0], acc1[P][1], a1, b1[P]);
+      }
     }
+  }
+#pragma unroll
+  for (int P = 0; P < NT; P++) {
+    acc[P][0] += acc1[P][0];
+    acc[P][1] += acc1[P][1];
   }
 }
 

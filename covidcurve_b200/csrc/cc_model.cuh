@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/covidcurve_b200.h"
+#include "cc_fastmath.cuh"
 
 namespace ccdev {
 
@@ -38,6 +39,7 @@ struct KModel {
   const double* pois_c;   // [T] -0.5*log(2*pi*x) - stirlerr(x) for x > 0, else 0   (x-only part of dpois)
   const double* lgx1;     // [T] lgamma(x+1)
   const double* logk;     // [T+1] log(k), k >= 1 (entry 0 unused): log of the integer days / lags
+  const LogTab* logtab;   // [128] table of fast_log (cc_fastmath.cuh)
   const double* rk;       // [max(T,640)+2] 1/k, k >= 1
   double l1_const;        // sum of lgamma(x+1) over the days that enter L1 (uncensored, observed, x >= 0)
   const int* l3_kind;     // [S*A] 0: skipped (pos == n == -1), 1: regular counts, 2: irregular -> R's full dbinom case analysis

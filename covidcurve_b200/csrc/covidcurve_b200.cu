@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_tile_k
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
-  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
+  const TileTables tb = tile_tables_load(m, reinterpret_cast<double*>(smem_raw));
+  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + tile_tables_doubles(m.T) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
   tile_smem_init(w);
   const long long gwarp = (long long)blockIdx.x * kWarpsPerCta + warp, nwarps = (long long)gridDim.x * kWarpsPerCta;
   double* scr = scratch + (size_t)gwarp * L.F * 32;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_tile_k
     if (v < n) tile_phase1<NT>(m, L, scr, lane, [&](int i) { return theta[(long long)i * ld + v]; });
     __syncwarp();
     const int cnt = (int)min((long long)32, n - v0);
-    for (int e = 0; e < cnt; e++) tile_phase2<NT>(m, L, w, scr, e);
+    for (int e = 0; e < cnt; e++) tile_phase2<NT>(m, L, w, tb, scr, e);
     __syncwarp();
     const double ll = tile_phase3(m, L, scr, lane, 0, 1, 32);
     if (v < n) out[v] = ll;
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_init_tile
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
-  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
+  const TileTables tb = tile_tables_load(m, reinterpret_cast<double*>(smem_raw));
+  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + tile_tables_doubles(m.T) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
   tile_smem_init(w);
   const TileLane tl = tile_lane(le);
   const int gwarp = blockIdx.x * kWarpsPerCta + warp, nwarps = gridDim.x * kWarpsPerCta;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_init_tile
     if (valid && tl.sub == 0) tile_phase1<NT>(m, L, scr, tl.e, par);
     __syncwarp();
     const int cnt = min(tl.E, P - p0);
-    for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, scr, q);
+    for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, tb, scr, q);
     __syncwarp();
     const double ll = tile_phase3(m, L, scr, tl.e, tl.sub, tl.G, tl.E);
     const double lp = tile_logprior(m, tl.sub, tl.G, tl.E, par);
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_sweep_til
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
-  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
+  const TileTables tb = tile_tables_load(m, reinterpret_cast<double*>(smem_raw));
+  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + tile_tables_doubles(m.T) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
   tile_smem_init(w);
   const TileLane tl = tile_lane(le);
   const int gwarp = blockIdx.x * kWarpsPerCta + warp, nwarps = gridDim.x * kWarpsPerCta;
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_sweep_til
       auto par = [&](int j) { return j == i ? thp : th[j]; };
       if (valid && tl.sub == 0) tile_phase1<NT>(m, L, scr, tl.e, par);
       __syncwarp();
-      for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, scr, q);
+      for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, tb, scr, q);
       __syncwarp();
       const double llp = tile_phase3(m, L, scr, tl.e, tl.sub, tl.G, tl.E);
       const double lpp = tile_logprior(m, tl.sub, tl.G, tl.E, par);
@@ -466,7 +469,9 @@ static int pick_nt(int T) {
 #undef CC_PICK
   return -1;
 }
-static size_t warp_cta_smem(const KModel& k, int nt) { return (size_t)kWarpsPerCta * tile_smem_doubles(k.K, k.A, k.S, nt) * sizeof(double); }
+static size_t warp_cta_smem(const KModel& k, int nt) {
+  return (tile_tables_doubles(k.T) + (size_t)kWarpsPerCta * tile_smem_doubles(k.K, k.A, k.S, nt)) * sizeof(double);
+}
 
 static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
   const int bytes = (int)warp_cta_smem(k, nt);
@@ -618,6 +623,12 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   }
   std::vector<double> logk(T + 1, 0.0);
   for (int i = 1; i <= T; i++) logk[i] = std::log((double)i);
+  std::vector<LogTab> logtab(128);
+  for (int i = 0; i < 128; i++) {
+    const float c = (float)(1.0 / (1.0 + ((double)i + 0.5) / 128.0));  // 24-bit reciprocal of the bin centre
+    logtab[i].c = (double)c;
+    logtab[i].mlogc = (double)(-logl((long double)c));
+  }
   std::vector<double> rk(std::max(T, 640) + 2, 0.0);
   for (size_t i = 1; i < rk.size(); i++) rk[i] = 1.0 / (double)i;
   {
@@ -642,7 +653,7 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   std::vector<double> p1(de->prior_p1, de->prior_p1 + d), p2(de->prior_p2, de->prior_p2 + d);
   int rc = CC_OK;
   if ((rc = upload(m, obsd, &k.obsd)) || (rc = upload(m, pois_c, &k.pois_c)) || (rc = upload(m, lgx1, &k.lgx1)) ||
-      (rc = upload(m, logk, &k.logk)) || (rc = upload(m, rk, &k.rk)) || (rc = upload(m, l3_kind, &k.l3_kind)) || (rc = upload(m, l3_lch, &k.l3_lchoose)) ||
+      (rc = upload(m, logk, &k.logk)) || (rc = upload(m, rk, &k.rk)) || (rc = upload(m, logtab, &k.logtab)) || (rc = upload(m, l3_kind, &k.l3_kind)) || (rc = upload(m, l3_lch, &k.l3_lchoose)) ||
       (rc = upload(m, sa, &k.sero_a)) || (rc = upload(m, sb, &k.sero_b)) || (rc = upload(m, pmin, &k.pmin)) ||
       (rc = upload(m, pmax, &k.pmax)) || (rc = upload(m, fam, &k.prior_family)) || (rc = upload(m, p1, &k.prior_p1)) ||
       (rc = upload(m, p2, &k.prior_p2))) {
@@ -1135,7 +1146,7 @@ extern "C" int cc_mcmc_diagnostics(cc_mcmc* r, double* beta, double* mc_accept, 
 
 // ------------------------------------------------------------------------------------------------ nmath test hook
 __global__ void nmath_kernel(int fn, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
-                             long long n, double* __restrict__ out) {
+                             long long n, double* __restrict__ out, const LogTab* __restrict__ tab) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double x = a[i], y = b[i], z = c[i];
@@ -1155,6 +1166,7 @@ __global__ void nmath_kernel(int fn, const double* __restrict__ a, const double*
     case CC_FN_PWEIBULL: r = pweibull_lower(x, y, z); break;
     case CC_FN_STIRLERR: r = stirlerr(x); break;
     case CC_FN_BD0: r = bd0(x, y); break;
+    case CC_FN_FASTLOG: r = fast_log(x, tab); break;
     default: r = d_nan();
   }
   out[i] = r;
@@ -1162,17 +1174,27 @@ __global__ void nmath_kernel(int fn, const double* __restrict__ a, const double*
 
 extern "C" int cc_nmath_batch(int device, int fn, const double* a, const double* b, const double* c, int64_t n, double* out) {
   if (!a || !b || !c || !out || n < 0) return fail(CC_E_INVALID, "cc_nmath_batch: bad argument");
-  if (fn < CC_FN_PGAMMA || fn > CC_FN_BD0) return fail(CC_E_INVALID, "cc_nmath_batch: unknown function id");
+  if (fn < CC_FN_PGAMMA || fn > CC_FN_FASTLOG) return fail(CC_E_INVALID, "cc_nmath_batch: unknown function id");
   if (cc_device_count() <= 0) return fail(CC_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
   if (n == 0) return CC_OK;
   CC_CUDA(cudaSetDevice(device));
   double* d = nullptr;
-  CC_CUDA(cudaMalloc((void**)&d, (size_t)4 * n * sizeof(double)));
+  CC_CUDA(cudaMalloc((void**)&d, (size_t)4 * n * sizeof(double) + 128 * sizeof(LogTab)));
+  LogTab* dtab = reinterpret_cast<LogTab*>(d + 4 * n);
+  {
+    LogTab ht[128];
+    for (int i = 0; i < 128; i++) {
+      const float cf = (float)(1.0 / (1.0 + ((double)i + 0.5) / 128.0));
+      ht[i].c = (double)cf;
+      ht[i].mlogc = (double)(-logl((long double)cf));
+    }
+    CC_CUDA(cudaMemcpy(dtab, ht, sizeof ht, cudaMemcpyHostToDevice));
+  }
   cudaError_t e = cudaMemcpy(d, a, n * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d + n, b, n * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d + 2 * n, c, n * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    nmath_kernel<<<(unsigned)((n + 127) / 128), 128>>>(fn, d, d + n, d + 2 * n, n, d + 3 * n);
+    nmath_kernel<<<(unsigned)((n + 127) / 128), 128>>>(fn, d, d + n, d + 2 * n, n, d + 3 * n, dtab);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost);

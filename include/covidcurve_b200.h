@@ -212,6 +212,7 @@ void cc_mcmc_destroy(cc_mcmc* s);
 #define CC_FN_PWEIBULL 7
 #define CC_FN_STIRLERR 8
 #define CC_FN_BD0 9
+#define CC_FN_FASTLOG 10 /* the table-driven log of the Poisson hot loop (csrc/cc_fastmath.cuh), a = argument */
 int cc_nmath_batch(int device, int fn, const double* a, const double* b, const double* c, int64_t n, double* out);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -183,3 +183,25 @@ def test_curves_match_oracle_intermediates(built_lib, modfit):
         for s in range(spec.S):
             w = cv["sero_full"][r][spec.sero_survey_start[s] - 1: spec.sero_survey_end[s]].mean()
             np.testing.assert_allclose(w * cv["ne"][r], tr["sero_num"][s * spec.A:(s + 1) * spec.A], rtol=1e-10)
+
+
+def test_device_nmath_against_oracle_nmath(built_lib):
+    """The device restatements of R's nmath (and the table-driven log of the Poisson loop) element by element."""
+    from covidcurve_b200 import _lib
+    from oracle.oracle import lib
+    L = lib()
+    rng = np.random.default_rng(3)
+    x = np.floor(rng.uniform(0, 500, 4000)); lam = rng.uniform(1e-3, 600, 4000)
+    want = np.array([L.cco_dpois(a, b, 1) for a, b in zip(x, lam)])
+    np.testing.assert_allclose(_lib.nmath("dpois", x, lam), want, rtol=1e-12, atol=1e-12)
+    n = np.floor(rng.uniform(1, 3e6, 4000)); p = rng.uniform(1e-4, 0.9, 4000); k = np.floor(n * p * rng.uniform(0.5, 1.5, 4000).clip(0, 1 / p))
+    k = np.minimum(k, n)
+    want = np.array([L.cco_dbinom(a, b, c, 1) for a, b, c in zip(k, n, p)])
+    np.testing.assert_allclose(_lib.nmath("dbinom", k, n, p), want, rtol=1e-11, atol=1e-10)
+    sod = rng.uniform(0.03, 1.2, 3000); mod = rng.uniform(5, 40, 3000); day = np.floor(rng.uniform(0, 300, 3000))
+    want = np.array([L.cco_pgamma(d, 1 / s ** 2, mm * s ** 2, 1, 0) for d, s, mm in zip(day, sod, mod)])
+    np.testing.assert_allclose(_lib.nmath("pgamma", day, 1 / sod ** 2, mod * sod ** 2), want, rtol=1e-10, atol=1e-300)
+    xs = np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), rng.uniform(0.5, 2, 20000), [1.0, 5e-324, 1e-310, np.inf]])
+    got = _lib.nmath("fastlog", xs)
+    assert np.max(np.abs(got[:-1] - np.log(xs[:-1])) / np.maximum(1.0, np.abs(np.log(xs[:-1])))) < 5e-16
+    assert got[-1] == np.inf and np.isnan(_lib.nmath("fastlog", np.array([-1.0])))[0] and _lib.nmath("fastlog", np.array([0.0]))[0] == -np.inf
