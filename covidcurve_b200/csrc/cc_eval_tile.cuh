@@ -61,7 +61,8 @@ __device__ inline TileTables tile_tables_load(const KModel& m, double*) {
 struct TileSmem {
   double* rec;  // [n2 rounded] record of the vector being processed
   double* xs;   // padded series
-  double* gs;   // kernel / later the convolution output in day order
+  double* gs;   // 7 zeros + delay kernel
+  double* auc;  // convolution output in day order (the batch kernels alias it onto gs + 8 once the kernel is consumed)
   double* sk;   // CH prefix sums
   double* ctab; // [128] interval-mass coefficients
 };
@@ -74,6 +75,7 @@ __device__ inline TileSmem carve_tile(double* q, const RecLayout& L, int NT) {
   w.rec = q; q += (L.n2 + 3) & ~3;
   w.xs = q; q += 12 * (8 * NT + 7);
   w.gs = q; q += 64 * NT + 16;
+  w.auc = w.gs + 8;
   w.sk = q; q += 64 * NT + 4;
   w.ctab = q;
   return w;
@@ -90,12 +92,35 @@ __device__ __noinline__ double dbinom_log_shared(double x, double n, double p) {
 __device__ __forceinline__ double lgamma_shared(double x) { return lgamma(x); }
 
 // ------------------------------------------------------------------------------------------------ phase 1
-// `par(i)` returns parameter i of this lane's vector.  scr = tile scratch, field f of lane e at scr[f*32 + e].
-template <int NT, typename Par>
-__device__ inline void tile_phase1(const KModel& m, const RecLayout& L, double* __restrict__ scr, int e, Par par) {
-  const int K = m.K, A = m.A, T = m.T;
-  auto put = [&](int f, double v) { scr[f * 32 + e] = v; };
-  // ---- role map with the re-parameterisation lift (Agecpp2strings.R:277-355)
+// Scalar-per-vector pieces.  `par(i)` returns parameter i of the vector, `put(f, v)` stores record field f.
+// The pieces are independent so that the Metropolis step can redo only what a single-parameter proposal touches.
+
+// attack-rate weights (binomial.cpp:60-73), ne*ma, test characteristics
+template <typename Par, typename Put>
+__device__ inline void p1_weights(const KModel& m, const RecLayout& L, Par par, Put put) {
+  const int A = m.A;
+  double snm = 0.0, nedom = 0.0;
+  if (A > 1)
+    for (int a = 0; a < A; a++) nedom += par(m.idx_noise[a]) * (double)m.demog[a];
+  for (int a = 0; a < A; a++) {
+    const int r = m.idx_ifr[a];
+    double ma = par(r);
+    if (m.reparam_ifr && r != m.idx_max_ma) ma = ma * par(m.idx_max_ma);
+    const double ne = (A > 1) ? (par(m.idx_noise[a]) * (double)m.demog[a]) / nedom : (m.binomial ? 1.0 : 0.0);
+    put(L.ne + a, ne);
+    put(L.nm + a, ne * ma);
+    snm += ne * ma;
+  }
+  put(L.snm, snm);
+  put(L.sens, par(m.idx_sens));
+  put(L.spec, par(m.idx_spec));
+}
+
+// role map with the re-parameterisation lift (Agecpp2strings.R:277-355), knot order (binomial.cpp:88-96), natural cubic
+// spline by the tridiagonal sweep (binomial.cpp:102-139), interval-lag thresholds (binomial.cpp:153-159)
+template <typename Par, typename Put>
+__device__ inline bool p1_spline(const KModel& m, const RecLayout& L, Par par, Put put) {
+  const int K = m.K;
   double nx[kMaxK], ny[kMaxK];
   nx[0] = 1.0;
   for (int i = 0; i < K - 1; i++) {
@@ -110,126 +135,118 @@ __device__ inline void tile_phase1(const KModel& m, const RecLayout& L, double* 
     if (m.reparam_infxn && r != m.idx_rel_infxn) v = v * par(m.idx_rel_infxn);
     ny[i] = v;
   }
-  // ---- attack-rate weights (binomial.cpp:60-73) and ne*ma
-  double snm = 0.0;
-  {
-    double nedom = 0.0;
-    if (A > 1)
-      for (int a = 0; a < A; a++) nedom += par(m.idx_noise[a]) * (double)m.demog[a];
-    for (int a = 0; a < A; a++) {
-      const int r = m.idx_ifr[a];
-      double ma = par(r);
-      if (m.reparam_ifr && r != m.idx_max_ma) ma = ma * par(m.idx_max_ma);
-      const double ne = (A > 1) ? (par(m.idx_noise[a]) * (double)m.demog[a]) / nedom : (m.binomial ? 1.0 : 0.0);
-      put(L.ne + a, ne);
-      put(L.nm + a, ne * ma);
-      snm += ne * ma;
-    }
-  }
-  put(L.snm, snm);
-  put(L.sens, par(m.idx_sens));
-  put(L.spec, par(m.idx_spec));
-  // ---- knot order (binomial.cpp:88-96)
   bool ok = true;
   for (int i = 1; i < K; i++) ok = ok && (nx[i] > nx[i - 1]);
   put(L.flags, ok ? 1.0 : 0.0);
-  if (!ok) return;
-  // ---- natural cubic spline, tridiagonal sweep (binomial.cpp:102-139)
-  {
-    double z[kMaxK], kk[kMaxK], rden[kMaxK];
-    for (int i = 0; i < K - 1; i++) rden[i] = 1.0 / (nx[i + 1] - nx[i]);
-    z[0] = 0.0;
-    kk[0] = 0.0;
-    for (int i = 1; i < K - 1; i++) {
-      const double mm = 3.0 * rden[i] * (ny[i + 1] - ny[i]) - 3.0 * rden[i - 1] * (ny[i] - ny[i - 1]);
-      const double den_im1 = nx[i] - nx[i - 1];
-      const double rg = 1.0 / (2.0 * (nx[i + 1] - nx[i - 1]) - den_im1 * kk[i - 1]);
-      kk[i] = (nx[i + 1] - nx[i]) * rg;
-      z[i] = (mm - den_im1 * z[i - 1]) * rg;
-    }
-    double sp2n = 0.0;
-    for (int i = K - 2; i >= 0; i--) {
-      const double den = nx[i + 1] - nx[i];
-      const double sp2i = z[i] - kk[i] * sp2n;
-      const int o = L.spl + 5 * i;
-      put(o, nx[i]);
-      put(o + 1, ny[i]);
-      put(o + 2, (ny[i + 1] - ny[i]) * rden[i] - (den * (sp2n + 2.0 * sp2i)) * (1.0 / 3.0));
-      put(o + 3, sp2i);
-      put(o + 4, (sp2n - sp2i) * (1.0 / 3.0) * rden[i]);
-      sp2n = sp2i;
-    }
-    // interval-lag rule in closed form (binomial.cpp:153-159)
-    double c = 0.0;
-    for (int mI = 1; mI <= K - 2; mI++) {
-      c = fmax(c + 1.0, ceil(nx[mI]) - 1.0);
-      put(L.cday + mI - 1, c);
-    }
+  if (!ok) return false;
+  double z[kMaxK], kk[kMaxK], rden[kMaxK];
+  for (int i = 0; i < K - 1; i++) rden[i] = 1.0 / (nx[i + 1] - nx[i]);
+  z[0] = 0.0;
+  kk[0] = 0.0;
+  for (int i = 1; i < K - 1; i++) {
+    const double mm = 3.0 * rden[i] * (ny[i + 1] - ny[i]) - 3.0 * rden[i - 1] * (ny[i] - ny[i - 1]);
+    const double den_im1 = nx[i] - nx[i - 1];
+    const double rg = 1.0 / (2.0 * (nx[i + 1] - nx[i - 1]) - den_im1 * kk[i - 1]);
+    kk[i] = (nx[i + 1] - nx[i]) * rg;
+    z[i] = (mm - den_im1 * z[i - 1]) * rg;
   }
-  // ---- delay-kernel constants (see gamma_delay_kernel in cc_eval_warp.cuh for the scheme)
-  {
-    const double sod = par(m.idx_sod), mod = par(m.idx_mod);
-    const double alph = 1.0 / (sod * sod), scale = mod * (sod * sod);
-    constexpr int kTabCap = 12 * 8 * NT - 4;
-    bool fast = (m.gamma_mode == 0) && (alph > 0.0) && (scale > 0.0) && isfinite(alph) && isfinite(scale);
-    double h = 0.0, xT = 0.0, lgam_a = 0.0, lsc = 0.0, QT = 0.0;
-    int km = 0, nser = 0;
-    if (fast) {
-      h = 1.0 / scale;
-      xT = (double)T * h;
-      if (!(h <= 48.0) || !(xT >= 3.0)) fast = false;
-    }
-    if (fast) {
-      const double kmed = fmax(alph - 1.0 / 3.0, 0.0) * scale;
-      km = (kmed >= (double)T) ? T : max((int)ceil(kmed), 16);
-      km = min(km, T);
-      const double x = (double)km * h;
-      const double nstar = fmax(floor(x - alph), 0.0);
-      const double y = 41.5 / x;
-      const double v = y * (1.0 / 3.0) + sqrt(y * y * (1.0 / 9.0) + 2.0 * y);
-      const double nn = nstar + v * x + 4.0;
-      if (!(nn < (double)kTabCap)) fast = false;
-      else nser = (int)nn;
-    }
-    if (fast) {
-      lgam_a = lgamma_shared(alph);
-      lsc = log(scale);
-      if (km < T && xT < alph + 9.0 * sqrt(alph) + 45.0) {
-        // Q(x_T): Legendre continued fraction, forward recurrence
-        double Am1 = 1.0, Ac = xT + 1.0 - alph, Bm1 = 0.0, Bc = 1.0, f = Ac, prev = 0.0;
-        for (int n = 1; n < 600; n++) {
-          const double an = -(double)n * ((double)n - alph), bnn = xT + (double)(2 * n + 1) - alph;
-          const double An = fma(bnn, Ac, an * Am1), Bn = fma(bnn, Bc, an * Bm1);
-          Am1 = Ac; Ac = An; Bm1 = Bc; Bc = Bn;
-          if (fabs(Ac) > 1e200) { Ac *= 1e-200; Am1 *= 1e-200; Bc *= 1e-200; Bm1 *= 1e-200; }
-          if ((n & 1) == 0) {
-            f = Ac / Bc;
-            if (fabs(f - prev) <= 1e-16 * fabs(f)) break;
-            prev = f;
-          }
+  double sp2n = 0.0;
+  for (int i = K - 2; i >= 0; i--) {
+    const double den = nx[i + 1] - nx[i];
+    const double sp2i = z[i] - kk[i] * sp2n;
+    const int o = L.spl + 5 * i;
+    put(o, nx[i]);
+    put(o + 1, ny[i]);
+    put(o + 2, (ny[i + 1] - ny[i]) * rden[i] - (den * (sp2n + 2.0 * sp2i)) * (1.0 / 3.0));
+    put(o + 3, sp2i);
+    put(o + 4, (sp2n - sp2i) * (1.0 / 3.0) * rden[i]);
+    sp2n = sp2i;
+  }
+  double c = 0.0;
+  for (int mI = 1; mI <= K - 2; mI++) {
+    c = fmax(c + 1.0, ceil(nx[mI]) - 1.0);
+    put(L.cday + mI - 1, c);
+  }
+  return true;
+}
+
+// delay-kernel constants (scheme: tile_gamma below)
+template <int NT, typename Par, typename Put>
+__device__ inline void p1_gamma(const KModel& m, const RecLayout& L, Par par, Put put) {
+  const int T = m.T;
+  const double sod = par(m.idx_sod), mod = par(m.idx_mod);
+  const double alph = 1.0 / (sod * sod), scale = mod * (sod * sod);
+  constexpr int kTabCap = 12 * 8 * NT - 4;
+  bool fast = (m.gamma_mode == 0) && (alph > 0.0) && (scale > 0.0) && isfinite(alph) && isfinite(scale);
+  double h = 0.0, xT = 0.0, lgam_a = 0.0, lsc = 0.0, QT = 0.0;
+  int km = 0, nser = 0;
+  if (fast) {
+    h = 1.0 / scale;
+    xT = (double)T * h;
+    if (!(h <= 48.0) || !(xT >= 3.0)) fast = false;
+  }
+  if (fast) {
+    const double kmed = fmax(alph - 1.0 / 3.0, 0.0) * scale;
+    km = (kmed >= (double)T) ? T : max((int)ceil(kmed), 16);
+    km = min(km, T);
+    const double x = (double)km * h;
+    const double nstar = fmax(floor(x - alph), 0.0);
+    const double y = 41.5 / x;
+    const double v = y * (1.0 / 3.0) + sqrt(y * y * (1.0 / 9.0) + 2.0 * y);
+    const double nn = nstar + v * x + 4.0;
+    if (!(nn < (double)kTabCap)) fast = false;
+    else nser = (int)nn;
+  }
+  if (fast) {
+    lgam_a = lgamma_shared(alph);
+    lsc = log(scale);
+    if (km < T && xT < alph + 9.0 * sqrt(alph) + 45.0) {
+      // Q(x_T): Legendre continued fraction, forward recurrence
+      double Am1 = 1.0, Ac = xT + 1.0 - alph, Bm1 = 0.0, Bc = 1.0, f = Ac, prev = 0.0;
+      for (int n = 1; n < 600; n++) {
+        const double an = -(double)n * ((double)n - alph), bnn = xT + (double)(2 * n + 1) - alph;
+        const double An = fma(bnn, Ac, an * Am1), Bn = fma(bnn, Bc, an * Bm1);
+        Am1 = Ac; Ac = An; Bm1 = Bc; Bc = Bn;
+        if (fabs(Ac) > 1e200) { Ac *= 1e-200; Am1 *= 1e-200; Bc *= 1e-200; Bm1 *= 1e-200; }
+        if ((n & 1) == 0) {
+          f = Ac / Bc;
+          if (fabs(f - prev) <= 1e-16 * fabs(f)) break;
+          prev = f;
         }
-        QT = exp(alph * (m.logk[T] - lsc) - xT - lgam_a) / f;
       }
-    }
-    put(L.gam + 0, alph); put(L.gam + 1, scale); put(L.gam + 2, h); put(L.gam + 3, lgam_a); put(L.gam + 4, lsc);
-    put(L.gam + 5, (double)km); put(L.gam + 6, (double)nser); put(L.gam + 7, QT); put(L.gam + 8, fast ? 1.0 : 0.0);
-  }
-  // ---- sero constants (binomial.cpp:257-284)
-  {
-    const double rate = par(m.idx_rate);
-    put(L.sero, rate);
-    if (!m.serorev) {
-      const double g1 = -expm1(-1.0 / rate), g32 = -expm1(-32.0 / rate);
-      put(L.sero + 1, g1);
-      put(L.sero + 2, g32);
-      put(L.sero + 3, (g1 == 0.0) ? 0.0 : (1.0 - g1) / g1);
-    } else {
-      const double shape = par(m.idx_shape), wscale = par(m.idx_scale);
-      put(L.sero + 1, shape);
-      put(L.sero + 2, log(wscale));
-      put(L.sero + 3, (!(shape > 0.0) || !(wscale > 0.0)) ? 1.0 : 0.0);
+      QT = exp(alph * (m.logk[T] - lsc) - xT - lgam_a) / f;
     }
   }
+  put(L.gam + 0, alph); put(L.gam + 1, scale); put(L.gam + 2, h); put(L.gam + 3, lgam_a); put(L.gam + 4, lsc);
+  put(L.gam + 5, (double)km); put(L.gam + 6, (double)nser); put(L.gam + 7, QT); put(L.gam + 8, fast ? 1.0 : 0.0);
+}
+
+// sero constants (binomial.cpp:257-284)
+template <typename Par, typename Put>
+__device__ inline void p1_sero(const KModel& m, const RecLayout& L, Par par, Put put) {
+  const double rate = par(m.idx_rate);
+  put(L.sero, rate);
+  if (!m.serorev) {
+    const double g1 = -expm1(-1.0 / rate), g32 = -expm1(-32.0 / rate);
+    put(L.sero + 1, g1);
+    put(L.sero + 2, g32);
+    put(L.sero + 3, (g1 == 0.0) ? 0.0 : (1.0 - g1) / g1);
+  } else {
+    const double shape = par(m.idx_shape), wscale = par(m.idx_scale);
+    put(L.sero + 1, shape);
+    put(L.sero + 2, log(wscale));
+    put(L.sero + 3, (!(shape > 0.0) || !(wscale > 0.0)) ? 1.0 : 0.0);
+  }
+}
+
+// all of phase 1 for lane e of a tile; scr = tile scratch, field f of lane e at scr[f*32 + e]
+template <int NT, typename Par>
+__device__ inline void tile_phase1(const KModel& m, const RecLayout& L, double* __restrict__ scr, int e, Par par) {
+  auto put = [&](int f, double v) { scr[f * 32 + e] = v; };
+  p1_weights(m, L, par, put);
+  if (!p1_spline(m, L, par, put)) return;
+  p1_gamma<NT>(m, L, par, put);
+  p1_sero(m, L, par, put);
 }
 
 // ------------------------------------------------------------------------------------------------ phase 2 pieces
@@ -460,10 +477,136 @@ __device__ __forceinline__ void warp_sum4(double& a, double& b, double& c, doubl
   }
 }
 
+// ---- S5 infection curve: w.xs <- exp(spline) (zero beyond T); returns the warp-reduced total
+template <int NT>
+__device__ inline double stage_spline(const KModel& m, const RecLayout& L, const double* __restrict__ rec, double* __restrict__ xs) {
+  const int lane = threadIdx.x & 31, T = m.T, K = m.K;
+  double tot = 0.0;
+  // interval thresholds in registers (the common K = 5 has three); longer knot vectors fall back to shared memory
+  const double cd0 = (K > 2) ? rec[L.cday] : 1e300, cd1 = (K > 3) ? rec[L.cday + 1] : 1e300, cd2 = (K > 4) ? rec[L.cday + 2] : 1e300;
+  const double y0 = rec[L.spl + 1];
+#pragma unroll 2
+  for (int i = lane; i < 64 * NT; i += 32) {
+    double v = 0.0;
+    if (i < T) {
+      const double di = (double)i;
+      int j = ((cd0 < di) ? 1 : 0) + ((cd1 < di) ? 1 : 0) + ((cd2 < di) ? 1 : 0);
+      for (int mI = 3; mI < K - 2; mI++) j += (rec[L.cday + mI] < di) ? 1 : 0;
+      const double* c = rec + L.spl + 5 * j;
+      const double dx = (double)(i + 1) - c[0];
+      const double y = (i == 0) ? y0 : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
+      v = exp(y);
+      tot += v;
+    }
+    xs[xs_index(i)] = v;
+  }
+  return warp_sum(tot);
+}
+
+// ---- S6 population check (binomial.cpp:170-184), warp-uniform result
+__device__ inline bool stage_popn(const KModel& m, const RecLayout& L, const double* __restrict__ rec, double tot) {
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  for (int a = lane; a < m.A; a += 32) ok = ok && !(rec[L.ne + a] * tot > (double)m.demog[a]);
+  return __all_sync(0xffffffffu, ok);
+}
+
+// ---- S7 death-delay convolution on the tensor cores, then back to day order through shared memory
+template <int NT>
+__device__ inline void stage_conv(const KModel& m, const double* __restrict__ xs, const double* __restrict__ gs, double* aucs) {
+  const int lane = threadIdx.x & 31;
+  double auc[NT][2];
+  toeplitz_dmma<NT>(xs, gs, (m.T + 7) >> 3, auc);
+  __syncwarp();  // aucs may alias the kernel region
+  const int n = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int P = 0; P < NT; P++) {
+    aucs[64 * P + 16 * t + n] = auc[P][0];
+    aucs[64 * P + 16 * t + 8 + n] = auc[P][1];
+  }
+  __syncwarp();
+}
+
+// ---- S8 Poisson term, evaluated day by day (binomial.cpp:199-221): l1 (without the data-only constant), sum of expd over
+// all days, sum of auc over the uncensored days
+__device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, const double* __restrict__ aucs, double snm, double& l1,
+                                       double& s_all, double& s_unc) {
+  const int lane = threadIdx.x & 31, T = m.T;
+  double dummy = 0.0;
+  l1 = s_all = s_unc = 0.0;
+#pragma unroll 2
+  for (int j = lane; j < T; j += 32) {
+    const double a = aucs[j];
+    const double expd = a * snm;
+    s_all += expd;
+    if ((j + 1) < m.rcensor_day) {
+      s_unc += a;
+      const int x = tb.obsd[j];
+      if (x != -1) {
+        double lp;
+        if (!(expd >= 0.0)) lp = d_nan();        // NaN or negative mean -> NaN (R::dpois)
+        else if (x < 0) lp = -d_inf();
+        else if (x == 0) lp = -expd;
+        else lp = (double)x * fast_log(expd, m.logtab) - expd;  // - lgamma(x+1) is data only: m.l1_const
+        l1 += lp;
+      }
+    }
+  }
+  warp_sum4(l1, s_all, s_unc, dummy);
+}
+
+// ---- the same term factored for the Metropolis step: with expd_j = auc_j * snm,
+//   L1 = sum_{x_j>0} x_j log auc_j + (sum_{x_j>0} x_j) log snm - snm * sum_{observed} auc_j - const,
+// so proposals that only move snm (IFR and attack-rate parameters) cost O(1).  `irregular` (any observed day with a
+// non-positive / NaN auc, or a negative count) sends the caller back to stage_l1_direct.
+struct L1Sums { double s1, sa_obs, s_all_auc, s_unc; int irregular; };
+__device__ inline L1Sums stage_l1_sums(const KModel& m, const TileTables& tb, const double* __restrict__ aucs) {
+  const int lane = threadIdx.x & 31, T = m.T;
+  double s1 = 0.0, sa = 0.0, sall = 0.0, sunc = 0.0;
+  int irr = 0;
+#pragma unroll 2
+  for (int j = lane; j < T; j += 32) {
+    const double a = aucs[j];
+    sall += a;
+    if ((j + 1) < m.rcensor_day) {
+      sunc += a;
+      const int x = tb.obsd[j];
+      if (x != -1) {
+        if (!(a > 0.0) || x < 0) irr = 1;
+        sa += a;
+        if (x > 0) s1 = fma((double)x, fast_log(a, m.logtab), s1);
+      }
+    }
+  }
+  warp_sum4(s1, sa, sall, sunc);
+  L1Sums r;
+  r.s1 = s1; r.sa_obs = sa; r.s_all_auc = sall; r.s_unc = sunc;
+  r.irregular = __any_sync(0xffffffffu, irr) ? 1 : 0;
+  return r;
+}
+
+// ---- S11/S12 survey-window means of infxn (*) H through the prefix-summed hazard (binomial.cpp:288-311); put(s, mean)
+template <typename PutBase>
+__device__ inline void stage_surveys(const KModel& m, const double* __restrict__ xs, const double* __restrict__ sk, PutBase put) {
+  const int lane = threadIdx.x & 31;
+  for (int s = 0; s < m.S; s++) {
+    const int st = m.sero_start[s], en = m.sero_end[s];
+    double b = 0.0;
+#pragma unroll 2
+    for (int t = lane; t < en; t += 32) {
+      int lo = st - 1 - t;
+      lo = lo < 0 ? 0 : lo;
+      b = fma(xs[xs_index(t)], sk[en - t] - sk[lo], b);
+    }
+    b = warp_sum(b);
+    if (lane == 0) put(s, b / (double)(en - st + 1));
+  }
+}
+
 // phase 2 for vector e of the tile: per-day stages; writes o_status, o_l1, o_texpd, o_sunc, o_base[S] to the scratch
 template <int NT>
 __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr, int e) {
-  const int lane = threadIdx.x & 31, T = m.T, A = m.A, S = m.S;
+  const int lane = threadIdx.x & 31, T = m.T;
   __syncwarp();
   for (int f = lane; f < L.n2; f += 32) w.rec[f] = scr[f * 32 + e];
   __syncwarp();
@@ -471,115 +614,37 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
 
   tile_sero_prefix<NT>(m, L, w, tb);   // S10 (first: with seroreversion it borrows the series/kernel regions)
   tile_gamma<NT>(m, L, w, tb);         // S2
-
-  // ---- S5 infection curve + S6 population check
-  double tot = 0.0;
-  {
-    const int K = m.K;
-    // interval thresholds in registers (the common K = 5 has three); longer knot vectors fall back to shared memory
-    const double cd0 = (K > 2) ? w.rec[L.cday] : 1e300, cd1 = (K > 3) ? w.rec[L.cday + 1] : 1e300, cd2 = (K > 4) ? w.rec[L.cday + 2] : 1e300;
-    const double y0 = w.rec[L.spl + 1];
-#pragma unroll 2
-    for (int i = lane; i < 64 * NT; i += 32) {
-      double v = 0.0;
-      if (i < T) {
-        const double di = (double)i;
-        int j = ((cd0 < di) ? 1 : 0) + ((cd1 < di) ? 1 : 0) + ((cd2 < di) ? 1 : 0);
-        for (int mI = 3; mI < K - 2; mI++) j += (w.rec[L.cday + mI] < di) ? 1 : 0;
-        const double* c = w.rec + L.spl + 5 * j;
-        const double dx = (double)(i + 1) - c[0];
-        const double y = (i == 0) ? y0 : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
-        v = exp(y);
-        tot += v;
-      }
-      w.xs[xs_index(i)] = v;
-    }
-  }
-  tot = warp_sum(tot);
-  {
-    bool ok = true;
-    for (int a = lane; a < A; a += 32) ok = ok && !(w.rec[L.ne + a] * tot > (double)m.demog[a]);
-    ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) scr[L.o_status * 32 + e] = ok ? 0.0 : 1.0;
-    if (!ok) return;
-  }
+  const double tot = stage_spline<NT>(m, L, w.rec, w.xs);
+  const bool ok = stage_popn(m, L, w.rec, tot);
+  if (lane == 0) scr[L.o_status * 32 + e] = ok ? 0.0 : 1.0;
+  if (!ok) return;
   __syncwarp();
-
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
     for (int j = lane; j < T; j += 32) m.debug_dump[j] = w.gs[7 + j];
-  // ---- S7 death-delay convolution on the tensor cores, then back to day order through shared memory
-  {
-    double auc[NT][2];
-    toeplitz_dmma<NT>(w.xs, w.gs, (T + 7) >> 3, auc);
-    __syncwarp();
-    const int n = lane >> 2, t = lane & 3;
-    double* aucs = w.gs + 8;
-#pragma unroll
-    for (int P = 0; P < NT; P++) {
-      aucs[64 * P + 16 * t + n] = auc[P][0];
-      aucs[64 * P + 16 * t + 8 + n] = auc[P][1];
-    }
-  }
-  __syncwarp();
-
+  stage_conv<NT>(m, w.xs, w.gs, w.auc);
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
     for (int j = lane; j < T; j += 32) {
       m.debug_dump[T + j] = w.xs[xs_index(j)];
-      m.debug_dump[2 * T + j] = w.gs[8 + j];
+      m.debug_dump[2 * T + j] = w.auc[j];
       m.debug_dump[3 * T + j] = w.sk[min(j, m.M)];
     }
   }
-  // ---- S8 Poisson term
-  double l1 = 0.0, s_all = 0.0, s_unc = 0.0, dummy = 0.0;
-  {
-    const double snm = w.rec[L.snm];
-    const double* aucs = w.gs + 8;
-#pragma unroll 2
-    for (int j = lane; j < T; j += 32) {
-      const double a = aucs[j];
-      const double expd = a * snm;
-      s_all += expd;
-      if ((j + 1) < m.rcensor_day) {
-        s_unc += a;
-        const int x = tb.obsd[j];
-        if (x != -1) {
-          double lp;
-          if (!(expd >= 0.0)) lp = d_nan();        // NaN or negative mean -> NaN (R::dpois)
-          else if (x < 0) lp = -d_inf();
-          else if (x == 0) lp = -expd;
-          else lp = (double)x * fast_log(expd, m.logtab) - expd;  // - lgamma(x+1) is data only: m.l1_const
-          l1 += lp;
-        }
-      }
-    }
-  }
-  warp_sum4(l1, s_all, s_unc, dummy);
+  double l1, s_all, s_unc;
+  stage_l1_direct(m, tb, w.auc, w.rec[L.snm], l1, s_all, s_unc);
   if (lane == 0) {
     scr[L.o_l1 * 32 + e] = l1 - m.l1_const;
     scr[L.o_texpd * 32 + e] = s_all;
     scr[L.o_sunc * 32 + e] = s_unc;
   }
-
-  // ---- S11/S12 survey-window means of infxn (*) H through the prefix-summed hazard
-  for (int s = 0; s < S; s++) {
-    const int st = m.sero_start[s], en = m.sero_end[s];
-    double b = 0.0;
-#pragma unroll 2
-    for (int t = lane; t < en; t += 32) {
-      int lo = st - 1 - t;
-      lo = lo < 0 ? 0 : lo;
-      b = fma(w.xs[xs_index(t)], w.sk[en - t] - w.sk[lo], b);
-    }
-    b = warp_sum(b);
-    if (lane == 0) scr[(L.o_base + s) * 32 + e] = b / (double)(en - st + 1);
-  }
+  stage_surveys(m, w.xs, w.sk, [&](int s, double v) { scr[(L.o_base + s) * 32 + e] = v; });
 }
 
 // ------------------------------------------------------------------------------------------------ phase 3
 // G = 32 / E lanes cooperate on one vector: lane = sub * E + e; terms are strided over sub and xor-reduced over the high bits
-__device__ inline double tile_phase3(const KModel& m, const RecLayout& L, const double* __restrict__ scr, int e, int sub, int G, int E) {
+__device__ inline double tile_phase3(const KModel& m, const RecLayout& L, const double* __restrict__ scr, int e, int sub, int G, int E,
+                                   int stride = 32) {
   const int A = m.A, S = m.S;
-  auto get = [&](int f) { return scr[f * 32 + e]; };
+  auto get = [&](int f) { return scr[f * stride + e]; };
   const bool pass = get(L.flags) != 0.0 && get(L.o_status) == 0.0;
   double tail = 0.0;
   if (pass) {
@@ -621,6 +686,14 @@ __device__ inline double tile_phase3(const KModel& m, const RecLayout& L, const 
   double loglik = get(L.o_l1) + tail;
   if (!isfinite(loglik)) loglik = -CC_OVERFLO;
   return loglik;
+}
+
+// one term of the generated logprior
+__device__ __forceinline__ double prior_term(const KModel& m, int i, double x) {
+  const int fam = m.prior_family[i];
+  if (fam == CC_PRIOR_NONE) return 0.0;
+  const double a = m.prior_p1[i], b = m.prior_p2[i];
+  return (fam == CC_PRIOR_DUNIF) ? dunif_log(x, a, b) : (fam == CC_PRIOR_DNORM) ? dnorm_log(x, a, b) : dbeta_log(x, a, b);
 }
 
 // generated logprior for E vectors per warp: G lanes per vector, terms strided over sub (Agecpp2strings.R:66-219)

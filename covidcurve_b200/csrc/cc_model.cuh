@@ -41,6 +41,8 @@ struct KModel {
   const double* logk;     // [T+1] log(k), k >= 1 (entry 0 unused): log of the integer days / lags
   const LogTab* logtab;   // [128] table of fast_log (cc_fastmath.cuh)
   const double* rk;       // [max(T,640)+2] 1/k, k >= 1
+  const int* dep;         // [d] stages a proposal of parameter i invalidates (kDep* bits, Metropolis sweep)
+  double l1_sumx;         // sum of the observed counts x_j > 0 over the days that enter L1
   double l1_const;        // sum of lgamma(x+1) over the days that enter L1 (uncensored, observed, x >= 0)
   const int* l3_kind;     // [S*A] 0: skipped (pos == n == -1), 1: regular counts, 2: irregular -> R's full dbinom case analysis
   const double* l3_lchoose;  // [S*A] lchoose(n, pos) for regular counts

@@ -132,26 +132,81 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_init_tile
   }
 }
 
-// One sweep of d single-site Metropolis-Hastings updates for every (chain, rung); a warp owns E = 2^le particles.
+// ---- per-warp shared memory of the cached Metropolis sweep: current and proposed copies of the record and of every
+// per-day array, so that a single-parameter proposal recomputes only the stages it touches and a rejection costs nothing
+struct SweepSmem {
+  double *recA, *recB, *xsA, *xsB, *gsA, *gsB, *aucA, *aucB, *skA, *skB, *ctab, *pcur, *pterm;
+};
+__host__ __device__ inline size_t sweep_smem_doubles(int d, int K, int A, int S, int NT) {
+  const RecLayout L = rec_layout(K, A, S);
+  const size_t F = (size_t)((L.F + 3) & ~3), dp = (size_t)((d + 3) & ~3);
+  return 2 * F + 2 * (size_t)(12 * (8 * NT + 7)) + 2 * (size_t)(64 * NT + 16) + 2 * (size_t)(64 * NT) + 2 * (size_t)(64 * NT + 4) + 128 + dp + dp + 4;
+}
+__device__ inline SweepSmem carve_sweep(double* q, int d, const RecLayout& L, int NT) {
+  SweepSmem w;
+  const int F = (L.F + 3) & ~3, dp = (d + 3) & ~3;
+  w.recA = q; q += F; w.recB = q; q += F;
+  w.xsA = q; q += 12 * (8 * NT + 7); w.xsB = q; q += 12 * (8 * NT + 7);
+  w.gsA = q; q += 64 * NT + 16; w.gsB = q; q += 64 * NT + 16;
+  w.aucA = q; q += 64 * NT; w.aucB = q; q += 64 * NT;
+  w.skA = q; q += 64 * NT + 4; w.skB = q; q += 64 * NT + 4;
+  w.ctab = q; q += 128;
+  w.pcur = q; q += dp;
+  w.pterm = q;
+  return w;
+}
+
+enum : int { kDepWeights = 1, kDepSpline = 2, kDepGamma = 4, kDepSero = 8 };
+
+template <typename T>
+__device__ __forceinline__ void swap_ptr(T*& a, T*& b) { T* t = a; a = b; b = t; }
+
+// One sweep of d single-site Metropolis-Hastings updates for every (chain, rung); one warp per particle, walking particles.
+// Every per-day array of the particle's current state stays in shared memory across the d sub-steps; a proposal for
+// parameter i redoes only the stages that depend on it (m.dep[i]): the IFR / attack-rate / test parameters touch no
+// per-day stage at all, the knots skip the gamma table, mod/sod skip the spline, the seroconversion rate skips both.
+// Every cached quantity is a pure function of the current parameter vector, so the values equal a from-scratch evaluation.
 // `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_sweep_tile_kernel(const KModel m, const McmcState s, int iteration, int le,
-                                                                             double* __restrict__ scratch) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(const KModel m, const McmcState s, int iteration) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
-  const TileTables tb = tile_tables_load(m, reinterpret_cast<double*>(smem_raw));
-  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + tile_tables_doubles(m.T) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
-  tile_smem_init(w);
-  const TileLane tl = tile_lane(le);
-  const int gwarp = blockIdx.x * kWarpsPerCta + warp, nwarps = gridDim.x * kWarpsPerCta;
-  double* scr = scratch + (size_t)gwarp * L.F * 32;
   const int d = m.d;
+  SweepSmem w = carve_sweep(reinterpret_cast<double*>(smem_raw) + (size_t)warp * sweep_smem_doubles(d, m.K, m.A, m.S, NT), d, L, NT);
+  const TileTables tb = tile_tables_load(m, nullptr);
+  for (int i = lane; i < kXsLead; i += 32) w.xsA[i] = w.xsB[i] = 0.0;
+  if (lane < 7) w.gsA[lane] = w.gsB[lane] = 0.0;
+  __syncwarp();
+  const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
   const int P = s.n_chains * s.rungs;
   const bool adapt = s.adapt_in_sampling || iteration <= s.burnin;
-  for (int b0 = gwarp * tl.E; b0 < P; b0 += nwarps * tl.E) {
-    const int b = min(b0 + tl.e, P - 1);
-    const bool valid = (b0 + tl.e) < P;
+  auto view = [&](double* rec, double* xs, double* gs, double* auc, double* sk) {
+    TileSmem v;
+    v.rec = rec; v.xs = xs; v.gs = gs; v.auc = auc; v.sk = sk; v.ctab = w.ctab;
+    return v;
+  };
+  // Poisson term from the cached sums (or day by day when they do not apply), written into `rec`
+  auto finish_l1 = [&](double* rec, const L1Sums& q, const double* aucs) {
+    const double snm = rec[L.snm];
+    double l1, texpd;
+    if (!q.irregular && snm > 0.0 && isfinite(snm)) {
+      l1 = (q.s1 + m.l1_sumx * log(snm)) - snm * q.sa_obs;
+      texpd = snm * q.s_all_auc;
+    } else {
+      double su;
+      stage_l1_direct(m, tb, aucs, snm, l1, texpd, su);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      rec[L.o_l1] = l1 - m.l1_const;
+      rec[L.o_texpd] = texpd;
+      rec[L.o_sunc] = q.s_unc;
+    }
+    __syncwarp();
+  };
+
+  for (int b = gwarp; b < P; b += nwarps) {
     const int c = b / s.rungs, r = b - c * s.rungs;
     const int pid = s.at_rung[b];  // particle (within chain) sitting at rung position r
     const int p = c * s.rungs + pid;
@@ -163,48 +218,142 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_sweep_til
     int* bwi = s.bw_index + (size_t)slot * d;
     unsigned int* macc = s.move_acc + (size_t)b * d;
     double ll = s.ll[p], lp = s.lp[p];
-    const int cnt = min(tl.E, P - b0);
+
+    // ---- rebuild the caches of the current state (one full evaluation per particle and sweep)
+    __syncwarp();
+    for (int j = lane; j < d; j += 32) w.pcur[j] = th[j];
+    __syncwarp();
+    for (int j = lane; j < d; j += 32) w.pterm[j] = prior_term(m, j, w.pcur[j]);
+    if (lane < 3) w.pterm[d + lane] = (m.jac_rows[lane] >= 0) ? m.jac_counts[lane] * log(w.pcur[max(m.jac_rows[lane], 0)]) : 0.0;
+    if (lane == 0) {
+      auto parc = [&](int j) { return w.pcur[j]; };
+      auto putA = [&](int f, double v) { w.recA[f] = v; };
+      w.recA[L.o_status] = 0.0;
+      p1_weights(m, L, parc, putA);
+      if (p1_spline(m, L, parc, putA)) {
+        p1_gamma<NT>(m, L, parc, putA);
+        p1_sero(m, L, parc, putA);
+      }
+    }
+    __syncwarp();
+    double tot_cur = 0.0;
+    L1Sums sums_cur = {0.0, 0.0, 0.0, 0.0, 1};
+    if (w.recA[L.flags] != 0.0) {
+      tile_sero_prefix<NT>(m, L, view(w.recA, w.xsB, w.gsB, w.aucB, w.skA), tb);
+      tile_gamma<NT>(m, L, view(w.recA, w.xsB, w.gsA, w.aucB, w.skA), tb);
+      tot_cur = stage_spline<NT>(m, L, w.recA, w.xsA);
+      const bool ok = stage_popn(m, L, w.recA, tot_cur);
+      if (lane == 0) w.recA[L.o_status] = ok ? 0.0 : 1.0;
+      __syncwarp();
+      if (ok) {
+        stage_conv<NT>(m, w.xsA, w.gsA, w.aucA);
+        sums_cur = stage_l1_sums(m, tb, w.aucA);
+        stage_surveys(m, w.xsA, w.skA, [&](int sv, double v) { w.recA[L.o_base + sv] = v; });
+        finish_l1(w.recA, sums_cur, w.aucA);
+      }
+    }
+    __syncwarp();
+
     for (int i = 0; i < d; i++) {
-      // every lane of the particle's group computes the (cheap) proposal redundantly
+      const int dep = m.dep[i];
+      // every lane computes the (cheap) proposal redundantly
       const ccrng::Draw dr = ccrng::draw(s.seed, ccrng::kStreamMove, (uint32_t)(s.chain_offset + c), (uint32_t)pid,
                                          (uint32_t)iteration, (uint32_t)i);
       const double lo = m.pmin[i], hi = m.pmax[i];
       const int tt = trans_type(lo, hi);
-      const double th_old = th[i];
+      const double th_old = w.pcur[i];
       const double bwv = bw[i];
       const double php = ph[i] + bwv * dr.z;
       const double thp = phi_to_theta(tt, php, lo, hi);
       const double adj = mh_adjust(tt, th_old, thp, lo, hi);
-      auto par = [&](int j) { return j == i ? thp : th[j]; };
-      if (valid && tl.sub == 0) tile_phase1<NT>(m, L, scr, tl.e, par);
+      auto par = [&](int j) { return j == i ? thp : w.pcur[j]; };
+      for (int f = lane; f < L.F; f += 32) w.recB[f] = w.recA[f];
       __syncwarp();
-      for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, tb, scr, q);
-      __syncwarp();
-      const double llp = tile_phase3(m, L, scr, tl.e, tl.sub, tl.G, tl.E);
-      const double lpp = tile_logprior(m, tl.sub, tl.G, tl.E, par);
-      const double mh = beta * (llp - ll) + (lpp - lp) + adj;
-      const bool acc = log(dr.u) < mh;  // uniform over the particle's lane group
-      if (acc) {
-        ll = llp;
-        lp = lpp;
+      if (lane == 0) {
+        auto putB = [&](int f, double v) { w.recB[f] = v; };
+        if (dep & kDepWeights) p1_weights(m, L, par, putB);
+        bool ok = w.recB[L.flags] != 0.0;
+        if (dep & kDepSpline) ok = p1_spline(m, L, par, putB);
+        // a vector whose knots were disordered has no gamma / sero constants yet: build them when the knots come back
+        const bool need_all = ok && (w.recA[L.flags] == 0.0);
+        if (ok && ((dep & kDepGamma) || need_all)) p1_gamma<NT>(m, L, par, putB);
+        if (ok && ((dep & kDepSero) || need_all)) p1_sero(m, L, par, putB);
+        w.recB[L.o_status] = 0.0;
       }
       __syncwarp();
-      if (valid && tl.sub == 0) {
-        if (acc) {
-          th[i] = thp;
-          ph[i] = php;
-          macc[i] += 1u;
+      const bool valid = w.recB[L.flags] != 0.0;
+      const bool from_invalid = (w.recA[L.flags] == 0.0) || (w.recA[L.o_status] != 0.0);  // no usable caches: redo everything
+      const bool do_sero = valid && ((dep & kDepSero) || from_invalid);
+      const bool do_gamma = valid && ((dep & kDepGamma) || from_invalid);
+      const bool do_spline = valid && ((dep & kDepSpline) || from_invalid);
+      double* use_xs = w.xsA; double* use_gs = w.gsA; double* use_auc = w.aucA; double* use_sk = w.skA;
+      double tot_p = tot_cur;
+      L1Sums sums_p = sums_cur;
+      if (valid) {
+        if (do_sero) { tile_sero_prefix<NT>(m, L, view(w.recB, w.xsB, w.gsB, w.aucB, w.skB), tb); use_sk = w.skB; }
+        if (do_gamma) { tile_gamma<NT>(m, L, view(w.recB, w.xsB, w.gsB, w.aucB, w.skB), tb); use_gs = w.gsB; }
+        if (do_spline) { tot_p = stage_spline<NT>(m, L, w.recB, w.xsB); use_xs = w.xsB; }
+        const bool ok = stage_popn(m, L, w.recB, tot_p);
+        if (lane == 0) w.recB[L.o_status] = ok ? 0.0 : 1.0;
+        __syncwarp();
+        if (ok) {
+          if (do_spline || do_gamma) {
+            stage_conv<NT>(m, use_xs, use_gs, w.aucB);
+            use_auc = w.aucB;
+            sums_p = stage_l1_sums(m, tb, w.aucB);
+          }
+          if (do_spline || do_sero) stage_surveys(m, use_xs, use_sk, [&](int sv, double v) { w.recB[L.o_base + sv] = v; });
+          finish_l1(w.recB, sums_p, use_auc);
         }
-        if (adapt) {
+      }
+      __syncwarp();
+      const double llp = tile_phase3(m, L, w.recB, 0, lane, 32, 1, 1);
+      // prior: only term i (and a Jacobian term if i is a reference parameter) changes
+      double pt_new = 0.0, jac_new[3] = {0.0, 0.0, 0.0};
+      {
+        pt_new = prior_term(m, i, thp);
+#pragma unroll
+        for (int j = 0; j < 3; j++) jac_new[j] = (m.jac_rows[j] == i) ? m.jac_counts[j] * log(thp) : w.pterm[d + j];
+        double v = 0.0;
+        for (int j = lane; j < d; j += 32)
+          if (m.prior_family[j] != CC_PRIOR_NONE) v += (j == i) ? pt_new : w.pterm[j];
+        if (lane < 3 && m.jac_rows[lane] >= 0) v += (lane == 0) ? jac_new[0] : (lane == 1) ? jac_new[1] : jac_new[2];
+        v = warp_sum(v);
+        if (!isfinite(v)) v = -CC_OVERFLO;
+        pt_new = pt_new;  // (kept for the commit below)
+        const double lpp = v;
+        const double mh = beta * (llp - ll) + (lpp - lp) + adj;
+        const bool acc = log(dr.u) < mh;  // warp-uniform
+        __syncwarp();
+        if (acc) {
+          ll = llp;
+          lp = lpp;
+          swap_ptr(w.recA, w.recB);
+          if (use_xs == w.xsB) swap_ptr(w.xsA, w.xsB);
+          if (use_gs == w.gsB) swap_ptr(w.gsA, w.gsB);
+          if (use_auc == w.aucB) swap_ptr(w.aucA, w.aucB);
+          if (use_sk == w.skB) swap_ptr(w.skA, w.skB);
+          tot_cur = tot_p;
+          sums_cur = sums_p;
+          if (lane == 0) {
+            w.pcur[i] = thp;
+            w.pterm[i] = pt_new;
+            for (int j = 0; j < 3; j++) w.pterm[d + j] = jac_new[j];
+            th[i] = thp;
+            ph[i] = php;
+            macc[i] += 1u;
+          }
+        }
+        if (lane == 0 && adapt) {
           // Robbins-Monro on log(bw) towards a 0.234 acceptance rate
           const double step = acc ? (1.0 - 0.234) : -0.234;
           bw[i] = exp(log(bwv) + step / sqrt((double)bwi[i]));
           bwi[i] += 1;
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    if (valid && tl.sub == 0) {
+    if (lane == 0) {
       s.ll[p] = ll;
       s.lp[p] = lp;
     }
@@ -480,7 +629,7 @@ static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
   if (nt == NT_) {                                                                                                    \
     e = cudaFuncSetAttribute(loglike_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_cached_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
   }
   CC_FOR_EACH_NT(CC_OPT)
 #undef CC_OPT
@@ -636,6 +785,32 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
     for (int i = 0; i < T; i++)
       if ((i + 1) < k.rcensor_day && obsd[i] >= 0) c += lgammal((long double)obsd[i] + 1.0L);
     k.l1_const = (double)c;
+    double sx = 0.0;
+    for (int i = 0; i < T; i++)
+      if ((i + 1) < k.rcensor_day && obsd[i] > 0) sx += (double)obsd[i];
+    k.l1_sumx = sx;
+  }
+  std::vector<int> dep(d, 0);
+  {
+    auto mark = [&](int row, int bit) { if (row >= 0 && row < d) dep[row] |= bit; };
+    for (int a = 0; a < A; a++) {
+      mark(de->idx_ifr[a], kDepWeights);
+      if (A > 1) mark(de->idx_noise[a], kDepWeights);
+    }
+    mark(de->idx_sens, kDepWeights);
+    mark(de->idx_spec, kDepWeights);
+    if (de->reparam_ifr) mark(de->idx_max_ma, kDepWeights);
+    for (int i = 0; i < K - 1; i++) mark(de->idx_knots[i], kDepSpline);
+    for (int i = 0; i < K; i++) mark(de->idx_infxn[i], kDepSpline);
+    if (de->reparam_knots) mark(de->idx_rel_knot, kDepSpline);
+    if (de->reparam_infxn) mark(de->idx_rel_infxn, kDepSpline);
+    mark(de->idx_mod, kDepGamma);
+    mark(de->idx_sod, kDepGamma);
+    mark(de->idx_sero_con_rate, kDepSero);
+    if (de->account_serorev) {
+      mark(de->idx_sero_rev_shape, kDepSero);
+      mark(de->idx_sero_rev_scale, kDepSero);
+    }
   }
   std::vector<double> sa(de->sero_a, de->sero_a + (size_t)S * A), sb(de->sero_b, de->sero_b + (size_t)S * A);
   std::vector<int> l3_kind((size_t)S * A, 0);
@@ -653,7 +828,7 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   std::vector<double> p1(de->prior_p1, de->prior_p1 + d), p2(de->prior_p2, de->prior_p2 + d);
   int rc = CC_OK;
   if ((rc = upload(m, obsd, &k.obsd)) || (rc = upload(m, pois_c, &k.pois_c)) || (rc = upload(m, lgx1, &k.lgx1)) ||
-      (rc = upload(m, logk, &k.logk)) || (rc = upload(m, rk, &k.rk)) || (rc = upload(m, logtab, &k.logtab)) || (rc = upload(m, l3_kind, &k.l3_kind)) || (rc = upload(m, l3_lch, &k.l3_lchoose)) ||
+      (rc = upload(m, logk, &k.logk)) || (rc = upload(m, rk, &k.rk)) || (rc = upload(m, dep, &k.dep)) || (rc = upload(m, logtab, &k.logtab)) || (rc = upload(m, l3_kind, &k.l3_kind)) || (rc = upload(m, l3_lch, &k.l3_lchoose)) ||
       (rc = upload(m, sa, &k.sero_a)) || (rc = upload(m, sb, &k.sero_b)) || (rc = upload(m, pmin, &k.pmin)) ||
       (rc = upload(m, pmax, &k.pmax)) || (rc = upload(m, fam, &k.prior_family)) || (rc = upload(m, p1, &k.prior_p1)) ||
       (rc = upload(m, p2, &k.prior_p2))) {
@@ -908,7 +1083,10 @@ struct cc_mcmc {
   long long rows = 0;
   long long evals = 0;
   size_t smem = 0;
-  int le = 0;          // log2 of the particles per warp tile
+  int le = 0;          // log2 of the particles per warp tile (initial-state kernel)
+  int sweep_wpc = 4;   // warps per CTA, grid and shared memory of the cached sweep kernel
+  unsigned sweep_grid = 1;
+  size_t sweep_smem = 0;
   unsigned grid = 1;
   double* scratch = nullptr;
 };
@@ -1029,6 +1207,24 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
     r->le = le;
     const long long tiles = ((long long)P + (1 << le) - 1) >> le;
     r->grid = (unsigned)std::min<long long>((tiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)m->grid_max);
+    {
+      const size_t per_warp = sweep_smem_doubles(d, m->k.K, m->k.A, m->k.S, m->nt) * sizeof(double);
+      const size_t cap = 227 * 1024;
+      int best_wpc = 0, best_warps = 0;
+      for (int wpc = kWarpsPerCta; wpc >= 1; wpc >>= 1) {
+        const int ctas = (int)(cap / (per_warp * wpc));
+        const int warps = std::min(ctas * wpc, 16);
+        if (warps > best_warps) { best_warps = warps; best_wpc = wpc; }
+      }
+      if (best_wpc == 0) {
+        cc_mcmc_destroy(r);
+        return fail(CC_E_INVALID, "model too large for the shared memory of the Metropolis sweep kernel");
+      }
+      r->sweep_wpc = best_wpc;
+      r->sweep_smem = per_warp * best_wpc;
+      const long long ctas_per_sm = std::max<long long>(1, (long long)(cap / r->sweep_smem));
+      r->sweep_grid = (unsigned)std::min<long long>(((long long)P + best_wpc - 1) / best_wpc, ctas_per_sm * m->sm_count);
+    }
     const RecLayout L = rec_layout(m->k.K, m->k.A, m->k.S);
     if ((rc = dalloc(r, &r->scratch, (size_t)r->grid * kWarpsPerCta * L.F * 32, false))) {
       cc_mcmc_destroy(r);
@@ -1073,7 +1269,7 @@ extern "C" int cc_mcmc_advance(cc_mcmc* r, int32_t n_iter) {
     if (r->iteration >= total) return fail(CC_E_STATE, "cc_mcmc_advance: burnin + samples iterations already done");
     const int it = (int)(r->iteration + 1);
     switch (m->nt) {
-#define CC_LAUNCH(NT_) case NT_: mcmc_sweep_tile_kernel<NT_><<<r->grid, 32 * kWarpsPerCta, r->smem, m->stream>>>(m->k, s, it, r->le, r->scratch); break;
+#define CC_LAUNCH(NT_) case NT_: mcmc_sweep_cached_kernel<NT_><<<r->sweep_grid, 32 * r->sweep_wpc, r->sweep_smem, m->stream>>>(m->k, s, it); break;
       CC_FOR_EACH_NT(CC_LAUNCH)
 #undef CC_LAUNCH
       default: break;
