@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--vectors", type=int, default=1 << 20, help="parameter vectors per GPU per step")
     ap.add_argument("--ref-vectors", type=int, default=8192, help="vectors per step of the CPU reference arm")
     ap.add_argument("--mcmc-iters", type=int, default=30, help="timed MCMC iterations (0 = skip the MCMC leg)")
+    ap.add_argument("--mcmc-settle", type=int, default=100, help="untimed MCMC iterations before the timed ones")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -254,10 +255,11 @@ def main():
     if args.mcmc_iters > 0:
         chains, rungs = truth["chains"], truth["rungs"]
         init = np.tile(synth.true_theta(spec, truth), (chains, 1))
-        burn = args.mcmc_iters + 8
+        settle = args.mcmc_settle  # untimed iterations that let the Robbins-Monro bandwidths settle (bw starts at 1)
+        burn = args.mcmc_iters + settle + 4
         mc = _lib.Mcmc(model, burnin=burn, samples=0, rungs=rungs, chains=chains, chain_offset=rank * chains, seed=synth.SEED_MCMC,
                        record_rungs=False, init=init)
-        mc.advance(5)
+        mc.advance(settle)
         barrier()
         m0 = time.perf_counter()
         mc.advance(args.mcmc_iters)
@@ -267,7 +269,8 @@ def main():
         particles = chains * rungs * world
         mcmc = {"iter_per_sec_all_chains_x_rungs": particles * args.mcmc_iters / mdt, "chains_per_gpu": chains, "rungs": rungs,
                 "iterations_timed": args.mcmc_iters, "loglike_evals_per_sec": particles * args.mcmc_iters * d / mdt,
-                "ms_per_iteration": mdt / args.mcmc_iters * 1e3, "workload": "cfg3: 64 chains x 50 rungs per GPU, d=34"}
+                "ms_per_iteration": mdt / args.mcmc_iters * 1e3, "settle_iterations": settle,
+                "workload": "cfg3: 64 chains x 50 rungs per GPU, d=34 (one iteration = d single-site updates + coupling pass)"}
         mc.close()
 
     # ---------------------------------------------------------------- roofline + CPU baseline (rank 0)
@@ -276,6 +279,7 @@ def main():
         dmma_tf, _, _ = _lib.dmma_probe(local_rank, 8192, 0)
         peak_tf = max(dfma_tf, dmma_tf)
         falg = f_alg(spec)
+        alg_bytes = (8 * d + 8) * V
         flops_per_launch = falg * V * full_frac
         achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12
         peaks = {}
@@ -284,9 +288,12 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        alg_bytes = (8 * d + 8) * V
         roofline = {
-            "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+            "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+            # (profiles/r1_summary.md: 20.7 MB for 65 536 evaluations = 316 B per evaluation), scaled to this launch
+            "traffic": 316.0 * V, "traffic_source": "ncu capture at 65 536 vectors, per-evaluation bytes x vectors of this launch",
+            "algorithmic_bytes": float(alg_bytes),
             "kernel": "loglike_tile_kernel", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
             "peak_source": "max of cc_fp64_peak_probe (register-resident DFMA chains: %.2f) and cc_dmma_probe (mma.sync m8n8k4 f64: %.2f), measured "
                            "live in this run; MEASURED_PEAKS.json has no FP64 entry" % (dfma_tf, dmma_tf),

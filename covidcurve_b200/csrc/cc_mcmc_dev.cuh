@@ -35,9 +35,9 @@ __host__ __device__ inline double phi_to_theta(int tt, double ph, double lo, dou
 // log Jacobian ratio of the proposal in phi-space
 __host__ __device__ inline double mh_adjust(int tt, double th, double thp, double lo, double hi) {
   switch (tt) {
-    case 1: return log(hi - thp) - log(hi - th);
-    case 2: return log(thp - lo) - log(th - lo);
-    case 3: return log(hi - thp) + log(thp - lo) - log(hi - th) - log(th - lo);
+    case 1: return log((hi - thp) / (hi - th));
+    case 2: return log((thp - lo) / (th - lo));
+    case 3: return log(((hi - thp) * (thp - lo)) / ((hi - th) * (th - lo)));  // = the four-log form of drjacoby, one log
     default: return 0.0;
   }
 }

@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(co
         if (lane == 0 && adapt) {
           // Robbins-Monro on log(bw) towards a 0.234 acceptance rate
           const double step = acc ? (1.0 - 0.234) : -0.234;
-          bw[i] = exp(log(bwv) + step / sqrt((double)bwi[i]));
+          bw[i] = bwv * exp(step / sqrt((double)bwi[i]));  // = exp(log bw + step / sqrt(n))
           bwi[i] += 1;
         }
         __syncwarp();

@@ -33,13 +33,19 @@ __device__ __forceinline__ double stirlerr(double n) {
     if (nn == (double)(int)nn) return c_sferr_halves[(int)nn];
     return lgamma(n + 1.) - (n + 0.5) * log(n) + n - CC_LN_SQRT_2PI;
   }
-  double nn = n * n;
-  double r = 1.0 / nn;
-  if (n > 500) return (S0 - S1 * r) / n;
-  if (n > 80) return (S0 - (S1 - S2 * r) * r) / n;
-  if (n > 35) return (S0 - (S1 - (S2 - S3 * r) * r) * r) / n;
-  return (S0 - (S1 - (S2 - (S3 - S4 * r) * r) * r) * r) / n;
+  const double rn = 1.0 / n;  // one division; the series in 1/n^2 is evaluated with multiplications
+  const double r = rn * rn;
+  if (n > 500) return (S0 - S1 * r) * rn;
+  if (n > 80) return (S0 - (S1 - S2 * r) * r) * rn;
+  if (n > 35) return (S0 - (S1 - (S2 - S3 * r) * r) * r) * rn;
+  return (S0 - (S1 - (S2 - (S3 - S4 * r) * r) * r) * r) * rn;
 }
+
+// reciprocals of the odd numbers 3, 5, ..., 65 for the Taylor loop of bd0
+__device__ __constant__ double c_inv_odd[32] = {
+    1.0 / 3,  1.0 / 5,  1.0 / 7,  1.0 / 9,  1.0 / 11, 1.0 / 13, 1.0 / 15, 1.0 / 17, 1.0 / 19, 1.0 / 21, 1.0 / 23,
+    1.0 / 25, 1.0 / 27, 1.0 / 29, 1.0 / 31, 1.0 / 33, 1.0 / 35, 1.0 / 37, 1.0 / 39, 1.0 / 41, 1.0 / 43, 1.0 / 45,
+    1.0 / 47, 1.0 / 49, 1.0 / 51, 1.0 / 53, 1.0 / 55, 1.0 / 57, 1.0 / 59, 1.0 / 61, 1.0 / 63, 1.0 / 65};
 
 // bd0(x, np) = x log(x/np) + np - x, evaluated stably (Loader).
 __device__ __forceinline__ double bd0(double x, double np) {
@@ -50,11 +56,11 @@ __device__ __forceinline__ double bd0(double x, double np) {
     if (fabs(s) < DBL_MIN) return s;
     double ej = 2 * x * v;
     v = v * v;
-    // |v| < 0.01: ej shrinks by >= 100x per term, 12 terms reach 1e-24 relative; exit as soon as a term is absorbed
+    // |v| < 0.01: ej shrinks by >= 100x per term; exit as soon as a term is absorbed (R's loop, with 1/(2j+1) tabulated)
 #pragma unroll 1
     for (int j = 1; j < 1000; j++) {
       ej *= v;
-      double s1 = s + ej / (double)((j << 1) + 1);
+      const double s1 = (j <= 32) ? fma(ej, c_inv_odd[j - 1], s) : s + ej / (double)((j << 1) + 1);
       if (s1 == s) return s1;
       s = s1;
     }
