@@ -605,10 +605,11 @@ __device__ inline void stage_surveys(const KModel& m, const double* __restrict__
 
 // phase 2 for vector e of the tile: per-day stages; writes o_status, o_l1, o_texpd, o_sunc, o_base[S] to the scratch
 template <int NT>
-__device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr, int e) {
+__device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr, int e,
+                                   long long stride = 32) {
   const int lane = threadIdx.x & 31, T = m.T;
   __syncwarp();
-  for (int f = lane; f < L.n2; f += 32) w.rec[f] = scr[f * 32 + e];
+  for (int f = lane; f < L.n2; f += 32) w.rec[f] = scr[f * stride + e];
   __syncwarp();
   if (w.rec[L.flags] == 0.0) return;  // knots not increasing: phase 3 returns the failure value
 
@@ -616,7 +617,7 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   tile_gamma<NT>(m, L, w, tb);         // S2
   const double tot = stage_spline<NT>(m, L, w.rec, w.xs);
   const bool ok = stage_popn(m, L, w.rec, tot);
-  if (lane == 0) scr[L.o_status * 32 + e] = ok ? 0.0 : 1.0;
+  if (lane == 0) scr[L.o_status * stride + e] = ok ? 0.0 : 1.0;
   if (!ok) return;
   __syncwarp();
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
@@ -632,17 +633,17 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   double l1, s_all, s_unc;
   stage_l1_direct(m, tb, w.auc, w.rec[L.snm], l1, s_all, s_unc);
   if (lane == 0) {
-    scr[L.o_l1 * 32 + e] = l1 - m.l1_const;
-    scr[L.o_texpd * 32 + e] = s_all;
-    scr[L.o_sunc * 32 + e] = s_unc;
+    scr[L.o_l1 * stride + e] = l1 - m.l1_const;
+    scr[L.o_texpd * stride + e] = s_all;
+    scr[L.o_sunc * stride + e] = s_unc;
   }
-  stage_surveys(m, w.xs, w.sk, [&](int s, double v) { scr[(L.o_base + s) * 32 + e] = v; });
+  stage_surveys(m, w.xs, w.sk, [&](int s, double v) { scr[(L.o_base + s) * stride + e] = v; });
 }
 
 // ------------------------------------------------------------------------------------------------ phase 3
 // G = 32 / E lanes cooperate on one vector: lane = sub * E + e; terms are strided over sub and xor-reduced over the high bits
 __device__ inline double tile_phase3(const KModel& m, const RecLayout& L, const double* __restrict__ scr, int e, int sub, int G, int E,
-                                   int stride = 32) {
+                                   long long stride = 32) {
   const int A = m.A, S = m.S;
   auto get = [&](int f) { return scr[f * stride + e]; };
   const bool pass = get(L.flags) != 0.0 && get(L.o_status) == 0.0;

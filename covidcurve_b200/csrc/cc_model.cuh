@@ -74,7 +74,9 @@ struct cc_model {
   std::vector<double> pinit;
   int sm_count = 0;
   int grid_max = 1;                // resident CTAs of the evaluation kernel on this device
-  double* scratch[3] = {nullptr, nullptr, nullptr};  // record tiles: [0] device-pointer calls, [1],[2] the two host-path streams
-  size_t scratch_doubles = 0;
+  // work buffers of the batched likelihood, one set per launch slot ([0] device-pointer calls, [1],[2] the two host-path
+  // streams): records rec[F][cap], regime keys, permutation, histogram + cursors; grown on demand
+  struct Work { double* rec = nullptr; int* key = nullptr; int* perm = nullptr; unsigned int* counts = nullptr; long long cap = 0; };
+  Work work[3];
   int nt = 0;                      // 64-day output tiles per evaluation (template parameter of the warp kernels)
 };

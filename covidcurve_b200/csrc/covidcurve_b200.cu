@@ -82,6 +82,94 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_tile_k
   }
 }
 
+// ---- batched likelihood as a two-pass pipeline --------------------------------------------------------------------
+// pass A (one THREAD per vector): phase 1 -> record rec[f * cap + v] in global memory, a regime key, a histogram of the keys
+// pass B (tiny): bucket offsets, then a scatter that groups the vector indices by key (order within a bucket is irrelevant:
+//         every vector is evaluated independently, so the values do not depend on the permutation)
+// pass C (one WARP per vector, tiles of 32 positions of the permutation): phases 2 and 3.
+// Grouping by regime keeps the warps of an SM on the same code path (small gamma table / large table / general algorithm /
+// no per-day work at all), which is what keeps the instruction cache warm on heterogeneous batches: measured 37 -> see
+// profiles/r1_summary.md M evals/s on box-uniform vectors.
+constexpr int kNumKeys = 8;
+
+template <int NT>
+__global__ void __launch_bounds__(128) loglike_phase1_kernel(const KModel m, const double* __restrict__ theta, long long n, long long ld,
+                                                              double* __restrict__ rec, long long cap, int* __restrict__ key,
+                                                              unsigned int* __restrict__ counts) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const RecLayout L = rec_layout(m.K, m.A, m.S);
+  int k = -1;
+  if (v < n) {
+    auto par = [&](int i) { return theta[(long long)i * ld + v]; };
+    auto put = [&](int f, double x) { rec[(long long)f * cap + v] = x; };
+    put(L.o_status, 0.0);
+    p1_weights(m, L, par, put);
+    k = 0;  // knots not increasing: no per-day work
+    if (p1_spline(m, L, par, put)) {
+      p1_gamma<NT>(m, L, par, put);
+      p1_sero(m, L, par, put);
+      const double fast = rec[(long long)(L.gam + 8) * cap + v], h = rec[(long long)(L.gam + 2) * cap + v];
+      k = (fast == 0.0) ? 5 : (h <= 3.6) ? 1 : (h <= 16.0) ? 2 : (h <= 32.0) ? 3 : 4;
+    }
+    key[v] = k;
+  }
+  // warp-aggregated histogram
+  for (int q = 0; q < 6; q++) {
+    const unsigned mask = __ballot_sync(0xffffffffu, k == q);
+    if (mask && (threadIdx.x & 31) == (__ffs(mask) - 1)) atomicAdd(&counts[q], (unsigned)__popc(mask));
+  }
+}
+
+__global__ void bucket_offsets_kernel(const unsigned int* __restrict__ counts, unsigned int* __restrict__ cursor) {
+  // heavy regimes first, so that the long-running tiles start early and the tail of the launch is made of cheap ones
+  const int order[6] = {5, 4, 3, 2, 1, 0};
+  unsigned int run = 0;
+  for (int q = 0; q < 6; q++) {
+    cursor[order[q]] = run;
+    run += counts[order[q]];
+  }
+}
+
+__global__ void bucket_scatter_kernel(const int* __restrict__ key, long long n, unsigned int* __restrict__ cursor, int* __restrict__ perm) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (v < n) ? key[v] : -1;
+  for (int q = 0; q < 6; q++) {
+    const unsigned mask = __ballot_sync(0xffffffffu, k == q);
+    if (!mask) continue;
+    const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[q], (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (k == q) perm[base + __popc(mask & ((1u << lane) - 1))] = (int)v;
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_phase23_kernel(const KModel m, long long n, double* __restrict__ rec,
+                                                                                          long long cap, const int* __restrict__ perm,
+                                                                                          double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RecLayout L = rec_layout(m.K, m.A, m.S);
+  const TileTables tb = tile_tables_load(m, nullptr);
+  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
+  tile_smem_init(w);
+  const long long gwarp = (long long)blockIdx.x * kWarpsPerCta + warp, nwarps = (long long)gridDim.x * kWarpsPerCta;
+  for (long long t0 = gwarp * 32; t0 < n; t0 += nwarps * 32) {
+    const long long pos = t0 + lane;
+    const int vl = (pos < n) ? perm[pos] : 0;
+    const int cnt = (int)min((long long)32, n - t0);
+    for (int e = 0; e < cnt; e++) {
+      const long long v = __shfl_sync(0xffffffffu, vl, e);
+      tile_phase2<NT>(m, L, w, tb, rec + v, (int)0, cap);
+    }
+    __syncwarp();
+    const double ll = tile_phase3(m, L, rec + vl, 0, 0, 1, 32, (int)cap);
+    if (pos < n) out[vl] = ll;
+    __syncwarp();
+  }
+}
+
 // decode lane -> (vector e of the tile, sub-lane) for tiles of E = 2^le vectors
 struct TileLane { int e, sub, G, E; };
 __device__ __forceinline__ TileLane tile_lane(int le) {
@@ -628,6 +716,7 @@ static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
 #define CC_OPT(NT_)                                                                                                   \
   if (nt == NT_) {                                                                                                    \
     e = cudaFuncSetAttribute(loglike_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(loglike_phase23_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_cached_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
   }
@@ -851,7 +940,7 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
     int bps = 0;
     const size_t sm_bytes = warp_cta_smem(k, m->nt);
     switch (m->nt) {
-#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_tile_kernel<NT_>, 32 * kWarpsPerCta, sm_bytes); break;
+#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_phase23_kernel<NT_>, 32 * kWarpsPerCta, sm_bytes); break;
       CC_FOR_EACH_NT(CC_OCC)
 #undef CC_OCC
       default: break;
@@ -861,9 +950,6 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
       return fail(CC_E_INVALID, "model too large for one CTA's shared memory");
     }
     m->grid_max = std::max(1, bps) * m->sm_count;
-    const RecLayout L = rec_layout(K, A, S);
-    m->scratch_doubles = (size_t)m->grid_max * kWarpsPerCta * L.F * 32;
-    for (int q = 0; q < 3 && e == cudaSuccess; q++) e = cudaMalloc((void**)&m->scratch[q], m->scratch_doubles * sizeof(double));
   }
   const size_t smem = eval_smem_bytes(d, T, T);
   if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(curves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -894,8 +980,12 @@ extern "C" void cc_model_destroy(cc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   for (void* p : m->dev_allocs) cudaFree(p);
-  for (int q = 0; q < 3; q++)
-    if (m->scratch[q]) cudaFree(m->scratch[q]);
+  for (int q = 0; q < 3; q++) {
+    if (m->work[q].rec) cudaFree(m->work[q].rec);
+    if (m->work[q].key) cudaFree(m->work[q].key);
+    if (m->work[q].perm) cudaFree(m->work[q].perm);
+    if (m->work[q].counts) cudaFree(m->work[q].counts);
+  }
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->d_out) cudaFree(m->d_out);
   if (m->h_pin) cudaFreeHost(m->h_pin);
@@ -909,15 +999,45 @@ extern "C" void cc_model_destroy(cc_model* m) {
 }
 
 // ------------------------------------------------------------------------------------------------ batch calls
+static int ensure_work(cc_model* m, int slot, long long n) {
+  cc_model::Work& wk = m->work[slot];
+  if (!wk.counts) CC_CUDA(cudaMalloc((void**)&wk.counts, 2 * kNumKeys * sizeof(unsigned int)));
+  if (wk.cap >= n) return CC_OK;
+  if (wk.rec) cudaFree(wk.rec);
+  if (wk.key) cudaFree(wk.key);
+  if (wk.perm) cudaFree(wk.perm);
+  wk.rec = nullptr; wk.key = nullptr; wk.perm = nullptr; wk.cap = 0;
+  const long long cap = (n + 1023) & ~1023LL;
+  const RecLayout L = rec_layout(m->k.K, m->k.A, m->k.S);
+  CC_CUDA(cudaMalloc((void**)&wk.rec, (size_t)L.F * cap * sizeof(double)));
+  CC_CUDA(cudaMalloc((void**)&wk.key, (size_t)cap * sizeof(int)));
+  CC_CUDA(cudaMalloc((void**)&wk.perm, (size_t)cap * sizeof(int)));
+  wk.cap = cap;
+  return CC_OK;
+}
+
+// the batched likelihood: pass A (thread per vector) -> regime buckets -> pass C (warp per vector); 4 launches on one stream
 static int launch_loglike(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st, int slot) {
   const KModel& k = m->k;
+  if (n > 0x7fffffffLL) return fail(CC_E_INVALID, "batch too large (2^31 vectors per call)");
+  int rc = ensure_work(m, slot, n);
+  if (rc) return rc;
+  cc_model::Work& wk = m->work[slot];
+  unsigned int* counts = wk.counts;
+  unsigned int* cursor = wk.counts + kNumKeys;
+  CC_CUDA(cudaMemsetAsync(counts, 0, 2 * kNumKeys * sizeof(unsigned int), st));
+  const unsigned gridA = (unsigned)((n + 127) / 128);
   const size_t smem = warp_cta_smem(k, m->nt);
   const long long tiles = (n + 31) / 32;
-  const long long ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-  const unsigned grid = (unsigned)std::min<long long>(ctas, (long long)m->grid_max);
-  double* scr = m->scratch[slot];
+  const unsigned gridC = (unsigned)std::min<long long>((tiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)m->grid_max);
   switch (m->nt) {
-#define CC_LAUNCH(NT_) case NT_: loglike_tile_kernel<NT_><<<grid, 32 * kWarpsPerCta, smem, st>>>(k, d_theta, n, ld, d_out, scr); break;
+#define CC_LAUNCH(NT_)                                                                                                        \
+  case NT_:                                                                                                                   \
+    loglike_phase1_kernel<NT_><<<gridA, 128, 0, st>>>(k, d_theta, n, ld, wk.rec, wk.cap, wk.key, counts);                     \
+    bucket_offsets_kernel<<<1, 1, 0, st>>>(counts, cursor);                                                                   \
+    bucket_scatter_kernel<<<gridA, 128, 0, st>>>(wk.key, n, cursor, wk.perm);                                                 \
+    loglike_phase23_kernel<NT_><<<gridC, 32 * kWarpsPerCta, smem, st>>>(k, n, wk.rec, wk.cap, wk.perm, d_out);                \
+    break;
     CC_FOR_EACH_NT(CC_LAUNCH)
 #undef CC_LAUNCH
     default: return fail(CC_E_INVALID, "unsupported days_obsd for the instantiated kernels");
@@ -975,7 +1095,7 @@ static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long l
                               (size_t)cn * sizeof(double), (size_t)d, cudaMemcpyHostToDevice, st[q]));
     rc = fn(m, dth, cn, chunk, dout, st[q], 1 + q);
     if (rc) return rc;
-    m->last_launches++;
+    m->last_launches += 4;
     CC_CUDA(cudaMemcpyAsync(out + c0, dout, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost, st[q]));
   }
   CC_CUDA(cudaEventRecord(m->ev_stage[1], st[1]));
@@ -1000,7 +1120,7 @@ static int batch_call(cc_model* m, launch_fn fn, const double* theta, int64_t n,
     int rc = fn(m, theta, n, ld, out, st, 0);
     if (rc) return rc;
     CC_CUDA(cudaEventRecord(m->ev1, st));
-    m->last_launches = 1;
+    m->last_launches = 4;
     m->last_ms = -1.0;  // resolved lazily by cc_last_kernel_ms
     return CC_OK;
   }
