@@ -322,7 +322,7 @@ def main():
                        "vectors_per_gpu_per_step": V, "layout": "SoA theta[d][V]", "l2": "inputs larger than L2 (%.0f MB per step)" % (d * V * 8 / 1e6),
                        "full_eval_fraction": full_frac},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": d * V * 8, "d2h_bytes_per_step": V * 8, "steps": e2e_steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * 5,  # phase-1 pass, bucket offsets, scatter, phase-2 pass, phase-3 pass per step
             "posterior_like": {"value": value_post, "unit": UNIT, "frac_of_fp64_peak": value_post * falg / 1e12 / peak_tf,
                                "vectors": "truth x (1 + 0.02 N(0,1)), clipped to the box"},
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "mcmc": mcmc,

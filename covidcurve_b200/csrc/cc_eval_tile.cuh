@@ -534,20 +534,33 @@ __device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, co
   const int lane = threadIdx.x & 31, T = m.T;
   double dummy = 0.0;
   l1 = s_all = s_unc = 0.0;
+  // common case without branches: every observed day has a positive normal mean and a count >= 0
+  int odd = 0;
 #pragma unroll 2
   for (int j = lane; j < T; j += 32) {
     const double a = aucs[j];
     const double expd = a * snm;
+    const int x = tb.obsd[j];
+    const bool unc = (j + 1) < m.rcensor_day, use = unc && (x != -1);
+    const double lg = fast_log_normal(expd, m.logtab);
+    const double lp = (x > 0) ? fma((double)x, lg, -expd) : -expd;  // - lgamma(x+1) is data only: m.l1_const
+    odd |= (use && (!fast_log_ok(expd) || x < 0)) ? 1 : 0;
     s_all += expd;
-    if ((j + 1) < m.rcensor_day) {
-      s_unc += a;
+    s_unc += unc ? a : 0.0;
+    l1 += use ? lp : 0.0;
+  }
+  if (__any_sync(0xffffffffu, odd)) {
+    // some observed day has a zero / subnormal / negative / non-finite mean or a negative count: R's case analysis
+    l1 = 0.0;
+    for (int j = lane; j < T; j += 32) {
+      const double expd = aucs[j] * snm;
       const int x = tb.obsd[j];
-      if (x != -1) {
+      if ((j + 1) < m.rcensor_day && x != -1) {
         double lp;
         if (!(expd >= 0.0)) lp = d_nan();        // NaN or negative mean -> NaN (R::dpois)
         else if (x < 0) lp = -d_inf();
         else if (x == 0) lp = -expd;
-        else lp = (double)x * fast_log(expd, m.logtab) - expd;  // - lgamma(x+1) is data only: m.l1_const
+        else lp = (double)x * fast_log(expd, m.logtab) - expd;
         l1 += lp;
       }
     }

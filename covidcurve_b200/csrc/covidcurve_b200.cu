@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_tile_k
 // pass A (one THREAD per vector): phase 1 -> record rec[f * cap + v] in global memory, a regime key, a histogram of the keys
 // pass B (tiny): bucket offsets, then a scatter that groups the vector indices by key (order within a bucket is irrelevant:
 //         every vector is evaluated independently, so the values do not depend on the permutation)
-// pass C (one WARP per vector, tiles of 32 positions of the permutation): phases 2 and 3.
+// pass C (one WARP per vector, tiles of 32 positions of the permutation): phase 2, the per-day work.
+// pass D (one THREAD per vector): phase 3.
 // Grouping by regime keeps the warps of an SM on the same code path (small gamma table / large table / general algorithm /
 // no per-day work at all), which is what keeps the instruction cache warm on heterogeneous batches: measured 37 -> see
 // profiles/r1_summary.md M evals/s on box-uniform vectors.
@@ -145,9 +146,8 @@ __global__ void bucket_scatter_kernel(const int* __restrict__ key, long long n, 
 }
 
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_phase23_kernel(const KModel m, long long n, double* __restrict__ rec,
-                                                                                          long long cap, const int* __restrict__ perm,
-                                                                                          double* __restrict__ out) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_phase2_kernel(const KModel m, long long n, double* __restrict__ rec,
+                                                                                          long long cap, const int* __restrict__ perm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
@@ -164,10 +164,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_phase2
       tile_phase2<NT>(m, L, w, tb, rec + v, (int)0, cap);
     }
     __syncwarp();
-    const double ll = tile_phase3(m, L, rec + vl, 0, 0, 1, 32, (int)cap);
-    if (pos < n) out[vl] = ll;
-    __syncwarp();
   }
+}
+
+// pass D (one THREAD per vector, original order -> coalesced): chained binomial, serology term, total + clamp
+__global__ void __launch_bounds__(128) loglike_phase3_kernel(const KModel m, long long n, const double* __restrict__ rec, long long cap,
+                                                              double* __restrict__ out) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const RecLayout L = rec_layout(m.K, m.A, m.S);
+  // tile_phase3 with one lane per vector and no cross-lane reduction (E = 32)
+  out[v] = tile_phase3(m, L, rec + v, 0, 0, 1, 32, cap);
 }
 
 // decode lane -> (vector e of the tile, sub-lane) for tiles of E = 2^le vectors
@@ -716,7 +723,7 @@ static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
 #define CC_OPT(NT_)                                                                                                   \
   if (nt == NT_) {                                                                                                    \
     e = cudaFuncSetAttribute(loglike_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(loglike_phase23_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_cached_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
   }
@@ -940,7 +947,7 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
     int bps = 0;
     const size_t sm_bytes = warp_cta_smem(k, m->nt);
     switch (m->nt) {
-#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_phase23_kernel<NT_>, 32 * kWarpsPerCta, sm_bytes); break;
+#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_phase2_kernel<NT_>, 32 * kWarpsPerCta, sm_bytes); break;
       CC_FOR_EACH_NT(CC_OCC)
 #undef CC_OCC
       default: break;
@@ -1036,7 +1043,8 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
     loglike_phase1_kernel<NT_><<<gridA, 128, 0, st>>>(k, d_theta, n, ld, wk.rec, wk.cap, wk.key, counts);                     \
     bucket_offsets_kernel<<<1, 1, 0, st>>>(counts, cursor);                                                                   \
     bucket_scatter_kernel<<<gridA, 128, 0, st>>>(wk.key, n, cursor, wk.perm);                                                 \
-    loglike_phase23_kernel<NT_><<<gridC, 32 * kWarpsPerCta, smem, st>>>(k, n, wk.rec, wk.cap, wk.perm, d_out);                \
+    loglike_phase2_kernel<NT_><<<gridC, 32 * kWarpsPerCta, smem, st>>>(k, n, wk.rec, wk.cap, wk.perm);                        \
+    loglike_phase3_kernel<<<gridA, 128, 0, st>>>(k, n, wk.rec, wk.cap, d_out);                                                \
     break;
     CC_FOR_EACH_NT(CC_LAUNCH)
 #undef CC_LAUNCH
@@ -1079,8 +1087,10 @@ typedef int (*launch_fn)(cc_model*, const double*, long long, long long, double*
 // pageable memory still works (the driver stages it).
 static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long long n, long long ld, double* out) {
   const int d = m->k.d;
-  const long long kChunk = 1 << 16;
-  const long long chunk = std::min<long long>(n, kChunk);
+  // at least ~4 chunks in flight for large batches (copy/compute overlap), chunks large enough to fill the GPU
+  long long chunk = ((n + 3) / 4 + 1023) & ~1023LL;
+  chunk = std::min<long long>(std::max<long long>(chunk, 1 << 16), 1 << 18);
+  chunk = std::min<long long>(n, chunk);
   int rc = ensure_stage(m, (size_t)2 * d * chunk * sizeof(double), (size_t)2 * chunk * sizeof(double));
   if (rc) return rc;
   cudaStream_t st[2] = {m->stream, m->stream2};
@@ -1095,7 +1105,7 @@ static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long l
                               (size_t)cn * sizeof(double), (size_t)d, cudaMemcpyHostToDevice, st[q]));
     rc = fn(m, dth, cn, chunk, dout, st[q], 1 + q);
     if (rc) return rc;
-    m->last_launches += 4;
+    m->last_launches += 5;
     CC_CUDA(cudaMemcpyAsync(out + c0, dout, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost, st[q]));
   }
   CC_CUDA(cudaEventRecord(m->ev_stage[1], st[1]));
@@ -1120,7 +1130,7 @@ static int batch_call(cc_model* m, launch_fn fn, const double* theta, int64_t n,
     int rc = fn(m, theta, n, ld, out, st, 0);
     if (rc) return rc;
     CC_CUDA(cudaEventRecord(m->ev1, st));
-    m->last_launches = 4;
+    m->last_launches = 5;
     m->last_ms = -1.0;  // resolved lazily by cc_last_kernel_ms
     return CC_OK;
   }
