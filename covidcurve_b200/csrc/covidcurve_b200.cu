@@ -56,32 +56,6 @@ constexpr int kWarpsPerCta = 4;
 #define CC_MIN_CTAS 4  // resident CTAs per SM the evaluation kernels are compiled for (caps registers at 128 per thread)
 #endif
 
-// Tile-phased evaluation (cc_eval_tile.cuh): each warp walks tiles of 32 consecutive parameter vectors.
-// theta is structure-of-arrays [d][ld]; scratch holds one record tile (F x 32 doubles) per warp of the grid.
-template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_tile_kernel(const KModel m, const double* __restrict__ theta, long long n,
-                                                                          long long ld, double* __restrict__ out, double* __restrict__ scratch) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const RecLayout L = rec_layout(m.K, m.A, m.S);
-  const TileTables tb = tile_tables_load(m, reinterpret_cast<double*>(smem_raw));
-  const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + tile_tables_doubles(m.T) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
-  tile_smem_init(w);
-  const long long gwarp = (long long)blockIdx.x * kWarpsPerCta + warp, nwarps = (long long)gridDim.x * kWarpsPerCta;
-  double* scr = scratch + (size_t)gwarp * L.F * 32;
-  for (long long v0 = gwarp * 32; v0 < n; v0 += nwarps * 32) {
-    const long long v = v0 + lane;
-    if (v < n) tile_phase1<NT>(m, L, scr, lane, [&](int i) { return theta[(long long)i * ld + v]; });
-    __syncwarp();
-    const int cnt = (int)min((long long)32, n - v0);
-    for (int e = 0; e < cnt; e++) tile_phase2<NT>(m, L, w, tb, scr, e);
-    __syncwarp();
-    const double ll = tile_phase3(m, L, scr, lane, 0, 1, 32);
-    if (v < n) out[v] = ll;
-    __syncwarp();
-  }
-}
-
 // ---- batched likelihood as a two-pass pipeline --------------------------------------------------------------------
 // pass A (one THREAD per vector): phase 1 -> record rec[f * cap + v] in global memory, a regime key, a histogram of the keys
 // pass B (tiny): bucket offsets, then a scatter that groups the vector indices by key (order within a bucket is irrelevant:
@@ -455,20 +429,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(co
   }
 }
 
-// One CTA per parameter vector; theta is structure-of-arrays [d][ld].
-__global__ void __launch_bounds__(kEvalThreads) loglike_batch_kernel(const KModel m, const double* __restrict__ theta,
-                                                                     long long n, long long ld, double* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  EvalSmem sm = carve_smem(smem_raw, m.d, m.T, m.M);
-  for (long long v = blockIdx.x; v < n; v += gridDim.x) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < m.d; i += blockDim.x) sm.p[i] = theta[(long long)i * ld + v];
-    __syncthreads();
-    const double ll = block_loglike(m, sm);
-    if (threadIdx.x == 0) out[v] = ll;
-  }
-}
-
 // One thread per parameter vector (the prior is d cheap terms).
 __global__ void logprior_batch_kernel(const KModel m, const double* __restrict__ theta, long long n, long long ld,
                                       double* __restrict__ out) {
@@ -514,108 +474,6 @@ __global__ void __launch_bounds__(kEvalThreads) curves_kernel(const KModel m, co
         __syncthreads();
       }
       for (int i = threadIdx.x; i < T; i += blockDim.x) o_sero[v * T + i] = conv_ok ? sm.tmp1[i] : d_nan();
-    }
-  }
-}
-
-// ---- MCMC kernels
-// initial state: phi, loglike, logprior of every particle
-__global__ void __launch_bounds__(kEvalThreads) mcmc_init_kernel(const KModel m, const McmcState s) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  EvalSmem sm = carve_smem(smem_raw, m.d, m.T, m.M);
-  const int P = s.n_chains * s.rungs;
-  for (int p = blockIdx.x; p < P; p += gridDim.x) {
-    __syncthreads();
-    double* th = s.theta + (size_t)p * m.d;
-    for (int i = threadIdx.x; i < m.d; i += blockDim.x) {
-      const double t = th[i];
-      sm.p[i] = t;
-      const double lo = m.pmin[i], hi = m.pmax[i];
-      s.phi[(size_t)p * m.d + i] = theta_to_phi(trans_type(lo, hi), t, lo, hi);
-    }
-    __syncthreads();
-    const double ll = block_loglike(m, sm);
-    __syncthreads();
-    const double lp = block_logprior(m, sm.p, sm.red);
-    if (threadIdx.x == 0) {
-      s.ll[p] = ll;
-      s.lp[p] = lp;
-    }
-  }
-}
-
-// One sweep of d single-site Metropolis-Hastings updates for every (chain, rung); one CTA per particle.
-// `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
-__global__ void __launch_bounds__(kEvalThreads) mcmc_sweep_kernel(const KModel m, const McmcState s, int iteration) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  EvalSmem sm = carve_smem(smem_raw, m.d, m.T, m.M);
-  __shared__ double sh_prop[4];  // theta', phi', adj, u
-  const int d = m.d;
-  const int P = s.n_chains * s.rungs;
-  const bool adapt = s.adapt_in_sampling || iteration <= s.burnin;
-  for (int b = blockIdx.x; b < P; b += gridDim.x) {
-    const int c = b / s.rungs, r = b - c * s.rungs;
-    const int pid = s.at_rung[b];            // particle (within chain) sitting at rung position r
-    const int p = c * s.rungs + pid;
-    const int slot = s.bw_per_particle ? p : b;
-    const double beta = s.beta[r];
-    double* th = s.theta + (size_t)p * d;
-    double* ph = s.phi + (size_t)p * d;
-    double* bw = s.bw + (size_t)slot * d;
-    int* bwi = s.bw_index + (size_t)slot * d;
-    unsigned int* macc = s.move_acc + (size_t)b * d;
-    __syncthreads();
-    for (int i = threadIdx.x; i < d; i += blockDim.x) sm.p[i] = th[i];
-    double ll = s.ll[p], lp = s.lp[p];
-    __syncthreads();
-    for (int i = 0; i < d; i++) {
-      if (threadIdx.x == 0) {
-        const ccrng::Draw dr = ccrng::draw(s.seed, ccrng::kStreamMove, (uint32_t)(s.chain_offset + c), (uint32_t)pid,
-                                           (uint32_t)iteration, (uint32_t)i);
-        const double lo = m.pmin[i], hi = m.pmax[i];
-        const int tt = trans_type(lo, hi);
-        const double php = ph[i] + bw[i] * dr.z;
-        const double thp = phi_to_theta(tt, php, lo, hi);
-        sh_prop[0] = thp;
-        sh_prop[1] = php;
-        sh_prop[2] = mh_adjust(tt, sm.p[i], thp, lo, hi);
-        sh_prop[3] = dr.u;
-      }
-      __syncthreads();
-      const double th_old = sm.p[i];
-      __syncthreads();
-      if (threadIdx.x == 0) sm.p[i] = sh_prop[0];
-      __syncthreads();
-      const double llp = block_loglike(m, sm);
-      __syncthreads();
-      const double lpp = block_logprior(m, sm.p, sm.red);
-      const double mh = beta * (llp - ll) + (lpp - lp) + sh_prop[2];
-      const bool acc = log(sh_prop[3]) < mh;  // block-uniform: every thread holds the same values
-      if (acc) {
-        ll = llp;
-        lp = lpp;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        if (acc) {
-          ph[i] = sh_prop[1];
-          macc[i] += 1u;
-        } else {
-          sm.p[i] = th_old;
-        }
-        if (adapt) {
-          // Robbins-Monro on log(bw) towards a 0.234 acceptance rate
-          const double step = acc ? (1.0 - 0.234) : -0.234;
-          bw[i] = exp(log(bw[i]) + step / sqrt((double)bwi[i]));
-          bwi[i] += 1;
-        }
-      }
-      __syncthreads();
-    }
-    for (int i = threadIdx.x; i < d; i += blockDim.x) th[i] = sm.p[i];
-    if (threadIdx.x == 0) {
-      s.ll[p] = ll;
-      s.lp[p] = lp;
     }
   }
 }
@@ -722,8 +580,7 @@ static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
   cudaError_t e = cudaSuccess;
 #define CC_OPT(NT_)                                                                                                   \
   if (nt == NT_) {                                                                                                    \
-    e = cudaFuncSetAttribute(loglike_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
+    e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_cached_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
   }
