@@ -294,7 +294,7 @@ def main():
             # (profiles/r1_summary.md: 20.7 MB for 65 536 evaluations = 316 B per evaluation), scaled to this launch
             "traffic": 316.0 * V, "traffic_source": "ncu capture at 65 536 vectors, per-evaluation bytes x vectors of this launch",
             "algorithmic_bytes": float(alg_bytes),
-            "kernel": "loglike_tile_kernel", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
+            "kernel": "loglike_phase2_kernel (the per-day pass; kernel_ms covers the whole 5-launch pipeline of one cc_loglike_batch call)", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
             "peak_source": "max of cc_fp64_peak_probe (register-resident DFMA chains: %.2f) and cc_dmma_probe (mma.sync m8n8k4 f64: %.2f), measured "
                            "live in this run; MEASURED_PEAKS.json has no FP64 entry" % (dfma_tf, dmma_tf),
             "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -36,6 +36,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__host__ __device__ inline int warp_tiles(int T) { return (T + 63) / 64; }  // 64-day output tiles of the Toeplitz product
+
 constexpr int kXsLead = 84;  // 7 zero blocks x 12 doubles in front of the padded series
 __device__ __forceinline__ int xs_index(int i) { return i + ((i >> 3) << 2) + kXsLead; }
 
