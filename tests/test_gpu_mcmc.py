@@ -108,3 +108,26 @@ def test_run_IFRmodel_age_api_shapes(built_lib, modfit):
     from covidcurve_b200 import summaries
     ci = summaries.get_cred_intervals(fit, "IFRparams", by_chain=False)
     assert list(ci["param"]) == spec.IFRparams and np.all(ci["LCI"] <= ci["UCI"])
+
+
+def test_posterior_curve_reevaluation(built_lib, modfit):
+    """draw_posterior_* (R/summarize_plot.R:276-884) batched through cc_curves_batch, checked against the oracle trace."""
+    import test_api_host
+    from covidcurve_b200 import api, posterior
+    from oracle.oracle import Oracle
+    spec, g = modfit
+    mdl = test_api_host._model_from(spec)
+    fit = api.run_IFRmodel_age(mdl, reparamIFR=True, reparamInfxn=True, reparamKnots=True, burnin=60, samples=60, rungs=1, chains=2, seed=8)
+    cd = posterior.draw_posterior_infxn_cubic_splines(fit, dwnsmpl=6, by_chain=True, by_strata=True)["curvedata"]
+    assert len(cd) == 6 * spec.T and {"chain", "sim", "time", "infxns_ma1", "infxns_ma3", "mod", "sod"} <= set(cd.columns)
+    sero = posterior.draw_posterior_sero_curves(fit, dwnsmpl=6)
+    deaths = posterior.posterior_check_infxns_to_death(fit, dwnsmpl=4)
+    assert len(sero) == 6 * spec.T and len(deaths) == 4 * spec.T and np.all(deaths["deaths_ma2"] >= 0)
+    # one draw against the oracle's intermediates (lifted-back parameters, reparam flags FALSE)
+    out = fit["mcmcout"]["output"]
+    row = out[(out["stage"] == "sampling") & (out["chain"] == "chain1")].iloc[-1]
+    th = row[spec.names].to_numpy(dtype=float)
+    tr = Oracle(spec).trace(th)
+    fit1 = {"inputs": fit["inputs"], "mcmcout": dict(fit["mcmcout"], output=out[(out["stage"] == "sampling") & (out["iteration"] == row["iteration"]) & (out["chain"] == "chain1")])}
+    one = posterior.draw_posterior_infxn_cubic_splines(fit1, dwnsmpl=1, by_strata=True)["curvedata"]
+    np.testing.assert_allclose(one["infxns_ma2"].to_numpy(), tr["ne"][1] * tr["infxn"], rtol=1e-11)

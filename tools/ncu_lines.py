@@ -37,7 +37,7 @@ for l in dis[start + 1:]:
     if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
         lines.append(cur)
         fresh = True
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ("loglike_tile" if "loglike" in kern else "mcmc_sweep")],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ("loglike_phase2" if "phase2" in kern else "mcmc_sweep" if "mcmc" in kern else "loglike")],
                      capture_output=True, text=True).stdout.splitlines()
 rows = list(csv.reader(out))
 hi = next(i for i, r in enumerate(rows) if "# Samples" in r)
