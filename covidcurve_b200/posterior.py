@@ -33,8 +33,11 @@ def _downsample(IFRmodel_inf, whichrung, dwnsmpl, seed):
     nodes = out[(out["stage"] == "sampling") & (out["rung"] == rung)].reset_index(drop=True)
     if dwnsmpl < 1 or dwnsmpl > len(nodes):
         raise ValueError("dwnsmpl must be between 1 and the number of sampling rows of the rung")
-    probs = convert_post_probs(nodes["loglikelihood"].to_numpy() + nodes["logprior"].to_numpy())
-    rows = np.sort(np.random.default_rng(seed).choice(len(nodes), size=int(dwnsmpl), replace=False, p=probs))
+    # sequential sampling without replacement, probability proportional to the posterior, done in log space (Gumbel
+    # top-k == R's ProbSampleNoReplace in distribution) so that rows whose probability underflows stay drawable
+    logpost = nodes["loglikelihood"].to_numpy(dtype=np.float64) + nodes["logprior"].to_numpy(dtype=np.float64)
+    keys = logpost + np.random.default_rng(seed).gumbel(size=len(nodes))
+    rows = np.sort(np.argsort(-keys, kind="stable")[: int(dwnsmpl)])
     return nodes.iloc[rows].reset_index(drop=True)
 
 

@@ -105,3 +105,27 @@ def test_gelman_rubin_and_ess_on_known_series():
 def test_rhat_from_moments_equals_rhat_from_draws():
     x = np.random.default_rng(1).normal(size=(5, 300, 3)) + np.arange(5)[:, None, None] * 0.1
     np.testing.assert_allclose(summaries.rhat_from_moments(*summaries.chain_moments(x)), summaries.rhat_per_parameter(x))
+
+
+def test_posterior_downsample_is_weighted_without_replacement():
+    """`sample(1:n, dwnsmpl, prob = convert_post_probs(logpost))` (R/summarize_plot.R:296-303): no repeats, increasing
+    row order, rows whose probability underflows in linear space are still reachable, high-posterior rows dominate."""
+    from covidcurve_b200 import posterior
+    n = 400
+    rng = np.random.default_rng(0)
+    ll = rng.normal(-500.0, 3.0, n)
+    ll[:50] -= 5000.0                                       # exp() underflows to exactly zero for these rows
+    out = pd.DataFrame({"chain": "chain1", "rung": "rung1", "iteration": np.arange(1, n + 1), "stage": "sampling",
+                        "logprior": np.zeros(n), "loglikelihood": ll})
+    fit = {"mcmcout": {"output": out, "diagnostics": {"rung_details": pd.DataFrame({"rung": [1], "thermodynamic_power": [1.0]})}}}
+    got = posterior._downsample(fit, None, 100, seed=3)
+    assert len(got) == 100 and got["iteration"].is_monotonic_increasing and got["iteration"].is_unique
+    assert (got["iteration"] > 50).all()
+    allrows = posterior._downsample(fit, None, n, seed=3)  # every row, including the underflowed ones
+    assert len(allrows) == n
+    top = np.argsort(-ll)[:40] + 1
+    hits = np.mean([np.isin(top, posterior._downsample(fit, None, 100, seed=s)["iteration"]).mean() for s in range(20)])
+    assert hits > 0.6                                       # uniform sampling would give 0.25
+    with pytest.raises(ValueError):
+        posterior._downsample(fit, None, n + 1, seed=3)
+    np.testing.assert_allclose(posterior.convert_post_probs(ll).sum(), 1.0, rtol=1e-12)
