@@ -13,6 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcovidcurve_b200.so")
+LIB_PATH = os.environ.get("CCB200_LIB", LIB_PATH)  # developer override: an alternative build of the same ABI
 
 CC_ABI_VERSION = 1
 CC_MEM_HOST, CC_MEM_DEVICE = 0, 1

@@ -312,6 +312,12 @@ def run_IFRmodel_age(IFRmodel, binomial_likelihood=True, reparamIFR=True, repara
     return {"class": "IFRmodel_inf", "inputs": inputs, "mcmcout": mcmcout}
 
 
+def save_fit_rds(IFRmodel_inf, path, compress=True):
+    """saveRDS(IFRmodel_inf, path): an R-readable fit object (covidcurve_b200/rdata.py; R side: r/ccb200.R ccb200_read_fit)."""
+    from . import rdata
+    rdata.write_fit_rds(path, IFRmodel_inf, compress=compress)
+
+
 def assemble_drjacoby_output(spec, draws, diag, burnin, samples, rungs, chains, coupling_on, GTI_pow, beta_manual, record_all_rungs=True,
                              cold_rung_last=True, chain_offset=0, rhat_fn=None):
     """`drjacoby_output` = list(output, diagnostics, parameters) (field list: SURVEY.md 8c).

@@ -207,9 +207,10 @@ __device__ __forceinline__ void causal_conv(const double* __restrict__ x, const 
 
 // ---------------------------------------------------------------------------------------------- the evaluation
 // All threads of the block call this with the parameter vector already in sm.p[0..d) and a __syncthreads()
-// behind it.  Returns the log-likelihood in every thread.  If `want_curves`, sm.infxn / sm.auc / sm.sc->ne are
-// left valid for the caller.
-__device__ inline double block_loglike(const KModel& m, EvalSmem& sm) {
+// behind it.  Returns the log-likelihood in every thread; sm.infxn / sm.auc / sm.haz / sm.sc->ne are left valid for the
+// caller.  `popn_exit` = false (curve extraction, R/summarize_plot.R:729 drops the population check) records a failed
+// population check in sc.popn_pass and carries on instead of returning the failure value.
+__device__ inline double block_loglike(const KModel& m, EvalSmem& sm, bool popn_exit = true) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int T = m.T, M = m.M, A = m.A, S = m.S;
   Scalars& sc = *sm.sc;
@@ -253,7 +254,8 @@ __device__ inline double block_loglike(const KModel& m, EvalSmem& sm) {
     int ok = 1;
     for (int a = 0; a < A; a++)
       if (sc.ne[a] * tot > (double)m.demog[a]) ok = 0;
-    if (!ok) return -CC_OVERFLO;  // block-uniform: every thread sees the same `tot`
+    if (!ok && popn_exit) return -CC_OVERFLO;  // block-uniform: every thread sees the same `tot`
+    if (!ok && tid == 0) sc.popn_pass = 0;
   }
 
   // ---- S7 death-delay convolution

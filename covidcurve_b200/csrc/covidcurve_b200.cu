@@ -55,6 +55,9 @@ constexpr int kWarpsPerCta = 4;
 #ifndef CC_MIN_CTAS
 #define CC_MIN_CTAS 4  // resident CTAs per SM the evaluation kernels are compiled for (caps registers at 128 per thread)
 #endif
+#ifndef CC_P2_CTAS
+#define CC_P2_CTAS CC_MIN_CTAS  // the same for pass C of the batched likelihood alone (developer experiments)
+#endif
 
 // ---- batched likelihood as a two-pass pipeline --------------------------------------------------------------------
 // pass A (one THREAD per vector): phase 1 -> record rec[f * cap + v] in global memory, a regime key, a histogram of the keys
@@ -65,7 +68,8 @@ constexpr int kWarpsPerCta = 4;
 // Grouping by regime keeps the warps of an SM on the same code path (small gamma table / large table / general algorithm /
 // no per-day work at all), which is what keeps the instruction cache warm on heterogeneous batches: measured 37 -> see
 // profiles/r1_summary.md M evals/s on box-uniform vectors.
-constexpr int kNumKeys = 8;
+constexpr int kNumKeys = 8;       // histogram slots; keys 0..5 are used, slot 6 is the phase-2 tile ticket
+constexpr int kPhase2Tile = 8;    // vectors per dynamically fetched tile of pass C
 
 template <int NT>
 __global__ void __launch_bounds__(128) loglike_phase1_kernel(const KModel m, const double* __restrict__ theta, long long n, long long ld,
@@ -120,19 +124,26 @@ __global__ void bucket_scatter_kernel(const int* __restrict__ key, long long n, 
 }
 
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) loglike_phase2_kernel(const KModel m, long long n, double* __restrict__ rec,
-                                                                                          long long cap, const int* __restrict__ perm) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_P2_CTAS) loglike_phase2_kernel(const KModel m, long long n, double* __restrict__ rec,
+                                                                                          long long cap, const int* __restrict__ perm,
+                                                                                          unsigned int* __restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
   const TileTables tb = tile_tables_load(m, nullptr);
   const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
   tile_smem_init(w);
-  const long long gwarp = (long long)blockIdx.x * kWarpsPerCta + warp, nwarps = (long long)gridDim.x * kWarpsPerCta;
-  for (long long t0 = gwarp * 32; t0 < n; t0 += nwarps * 32) {
+  // dynamic queue of kPhase2Tile-vector tiles in bucket order (heavy regimes first): a warp that drew cheap vectors comes
+  // back for more, so the launch ends within one short tile of the ideal instead of one 32-vector tile of the worst regime
+  for (;;) {
+    unsigned int tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    const long long t0 = (long long)tk * kPhase2Tile;
+    if (t0 >= n) break;
     const long long pos = t0 + lane;
-    const int vl = (pos < n) ? perm[pos] : 0;
-    const int cnt = (int)min((long long)32, n - t0);
+    const int vl = (lane < kPhase2Tile && pos < n) ? perm[pos] : 0;
+    const int cnt = (int)min((long long)kPhase2Tile, n - t0);
     for (int e = 0; e < cnt; e++) {
       const long long v = __shfl_sync(0xffffffffu, vl, e);
       tile_phase2<NT>(m, L, w, tb, rec + v, (int)0, cap);
@@ -453,12 +464,10 @@ __global__ void __launch_bounds__(kEvalThreads) curves_kernel(const KModel m, co
     __syncthreads();
     for (int i = threadIdx.x; i < m.d; i += blockDim.x) sm.p[i] = theta[(long long)i * ld + v];
     __syncthreads();
-    const double ll = block_loglike(mc, sm);
+    (void)block_loglike(mc, sm, false);
     __syncthreads();
-    const bool ok = sm.sc->nodex_pass && (ll != -CC_OVERFLO || true);
     // an invalid knot order leaves no curve: report NaN like an aborted evaluation would
     const bool have = sm.sc->nodex_pass != 0;
-    (void)ok;
     if (o_ne)
       for (int a = threadIdx.x; a < A; a += blockDim.x) o_ne[v * A + a] = sm.sc->ne[a];
     if (o_infxn)
@@ -467,13 +476,13 @@ __global__ void __launch_bounds__(kEvalThreads) curves_kernel(const KModel m, co
     if (o_auc)
       for (int i = threadIdx.x; i < T; i += blockDim.x) o_auc[v * T + i] = conv_ok ? sm.auc[i] : d_nan();
     if (o_sero) {
-      // sero_full[j] = sum_{i<=j} infxn[i] * haz[j-i]
-      if (conv_ok) {
+      // sero_full[j] = sum_{i<=j} infxn[i] * haz[j-i]; computed whether or not the population check passed (:729)
+      if (have) {
         __syncthreads();
         causal_conv(sm.infxn, sm.haz, T, sm.tmp1);
         __syncthreads();
       }
-      for (int i = threadIdx.x; i < T; i += blockDim.x) o_sero[v * T + i] = conv_ok ? sm.tmp1[i] : d_nan();
+      for (int i = threadIdx.x; i < T; i += blockDim.x) o_sero[v * T + i] = have ? sm.tmp1[i] : d_nan();
     }
   }
 }
@@ -892,7 +901,7 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
   CC_CUDA(cudaMemsetAsync(counts, 0, 2 * kNumKeys * sizeof(unsigned int), st));
   const unsigned gridA = (unsigned)((n + 127) / 128);
   const size_t smem = warp_cta_smem(k, m->nt);
-  const long long tiles = (n + 31) / 32;
+  const long long tiles = (n + kPhase2Tile - 1) / kPhase2Tile;
   const unsigned gridC = (unsigned)std::min<long long>((tiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)m->grid_max);
   switch (m->nt) {
 #define CC_LAUNCH(NT_)                                                                                                        \
@@ -900,7 +909,7 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
     loglike_phase1_kernel<NT_><<<gridA, 128, 0, st>>>(k, d_theta, n, ld, wk.rec, wk.cap, wk.key, counts);                     \
     bucket_offsets_kernel<<<1, 1, 0, st>>>(counts, cursor);                                                                   \
     bucket_scatter_kernel<<<gridA, 128, 0, st>>>(wk.key, n, cursor, wk.perm);                                                 \
-    loglike_phase2_kernel<NT_><<<gridC, 32 * kWarpsPerCta, smem, st>>>(k, n, wk.rec, wk.cap, wk.perm);                        \
+    loglike_phase2_kernel<NT_><<<gridC, 32 * kWarpsPerCta, smem, st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 6);                      \
     loglike_phase3_kernel<<<gridA, 128, 0, st>>>(k, n, wk.rec, wk.cap, d_out);                                                \
     break;
     CC_FOR_EACH_NT(CC_LAUNCH)

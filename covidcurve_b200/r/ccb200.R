@@ -85,3 +85,25 @@ ccb200_run_mcmc <- function(IFRmodel, data_list, misc_list, df_params, binomial_
   class(ret) <- "drjacoby_output"
   ret
 }
+
+# A fit written on a GPU box without R (covidcurve_b200/rdata.py: write_fit_rds) -> the `IFRmodel_inf` object every
+# function of R/summarize_plot.R takes.  `mcmcout` is already a drjacoby_output; `inputs$IFRmodel` arrives as a named
+# list of fields (class "IFRmodel_fields": an R6 object is an environment of closures and cannot be written without R)
+# and is rebuilt here through the public setters of R/model.R:192-355, in the order the setters' own checks require.
+ccb200_read_fit <- function(path) {
+  fit <- readRDS(path)
+  f <- fit$inputs$IFRmodel
+  if (!inherits(f, "IFRmodel_fields")) return(fit)
+  m <- COVIDCurve::make_IFRmodel_age$new()
+  m$set_MeanTODparam(f$modparam); m$set_CoefVarOnsetTODparam(f$sodparam)
+  m$set_IFRparams(f$IFRparams); m$set_maxMa(f$maxMa)
+  m$set_Knotparams(f$Knotparams); m$set_relKnot(f$relKnot)
+  m$set_Infxnparams(f$Infxnparams); m$set_relInfxn(f$relInfxn)
+  if (!is.null(f$Noiseparams)) m$set_Noiseparams(f$Noiseparams)
+  m$set_Serotestparams(f$Serotestparams)
+  m$set_data(f$data); m$set_demog(f$demog); m$set_paramdf(f$paramdf)
+  if (!is.null(f$rcensor_day)) m$set_rcensor_day(f$rcensor_day)
+  if (!is.null(f$IFRdictkey)) m$set_IFRdictkey(f$IFRdictkey)
+  fit$inputs$IFRmodel <- m
+  fit
+}

@@ -11,6 +11,10 @@ Outputs (committed, small):
         Also posterior summaries of the sampling stage (for statistical MCMC checks).
   tests/golden/simdata_golden.npz  - inputs of tests/testthat/test-check_natcub_cpp.R rebuilt
         from data/covidcurve_simdata.rda, both parameter vectors.
+  tests/golden/r403_stream.rda     - data/covidcurve_simdata.rda itself (13 kB, a byte stream written by R 4.0.3): the
+        known-answer vector of the R serialisation writer (parse -> re-serialise must reproduce it byte for byte).
+  tests/golden/modfit_schema.json  - field names / SEXP types / classes of the stored fit's `mcmcout` and `inputs`
+        (no values): what the fit-object writer must reproduce field for field.
 """
 import os
 import sys
@@ -156,5 +160,40 @@ def main():
     print("simdata: total deaths", deaths.sum(), "prop", prop, "pos", pos)
 
 
+def schema(o, depth=0):
+    """Names, SEXP types and classes of an object tree (values dropped; data-frame columns kept, long vectors cut)."""
+    if o is None:
+        return {"t": "NULL"}
+    if "env" in o:
+        return {"t": "env"}
+    a = o.get("attr", {})
+    d = {"t": o["t"], "len": len(o["v"]) if o["t"] != 19 else None}
+    if "class" in a:
+        d["class"] = list(a["class"]["v"])
+    if "row.names" in a:
+        d["compact_row_names"] = a["row.names"]["v"][0] == -2147483648
+    if o["t"] == 19:
+        d["names"] = list(a["names"]["v"])
+        d["items"] = [schema(v, depth + 1) for v in o["v"]]
+        del d["len"]
+    elif d["len"] > 64:
+        d["len"] = "n"
+    return d
+
+
+def extras():
+    import json
+    import shutil
+    shutil.copyfile(os.path.join(REF, "covidcurve_simdata.rda"), os.path.join(HERE, "r403_stream.rda"))
+    fit = load(os.path.join(REF, "covidcurve_modfit.rda"))["covidcurve_modfit"]
+    sch = {"class": list(fit["attr"]["class"]["v"]), "names": names(fit), "inputs": schema(get(fit, "inputs")),
+           "mcmcout": schema(get(fit, "mcmcout"))}
+    for node in (sch["mcmcout"]["items"][2]["items"][2], sch["mcmcout"]["items"][2]["items"][3]):
+        node["len"] = 1  # the generated C++ strings: one element each
+    with open(os.path.join(HERE, "modfit_schema.json"), "w") as f:
+        json.dump(sch, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
+    extras()

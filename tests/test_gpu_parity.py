@@ -183,6 +183,17 @@ def test_curves_match_oracle_intermediates(built_lib, modfit):
         for s in range(spec.S):
             w = cv["sero_full"][r][spec.sero_survey_start[s] - 1: spec.sero_survey_end[s]].mean()
             np.testing.assert_allclose(w * cv["ne"][r], tr["sero_num"][s * spec.A:(s + 1) * spec.A], rtol=1e-10)
+    # more infections than people: the likelihood exits early (no auc), the sero-curve extraction drops that check
+    # (R/summarize_plot.R:729) and an invalid knot order leaves no curve at all
+    big, bad = th[0].copy(), th[0].copy()
+    big[[spec.index(n) for n in spec.Infxnparams]] = 12.0
+    bad[spec.index("x1")] = 199.0
+    cv2 = m.curves(np.stack([big, bad, th[1]]))
+    assert np.isnan(cv2["auc"][0]).all() and np.isfinite(cv2["sero_full"][0]).all() and np.isfinite(cv2["infxn"][0]).all()
+    assert np.isnan(cv2["infxn"][1]).all() and np.isnan(cv2["sero_full"][1]).all() and np.isfinite(cv2["ne"][1]).all()
+    np.testing.assert_array_equal(cv2["sero_full"][2], cv["sero_full"][1])
+    hz = 1 - np.exp(-(np.arange(spec.T) + 1) / big[spec.index("sero_con_rate")])
+    np.testing.assert_allclose(cv2["sero_full"][0], np.convolve(cv2["infxn"][0], hz)[:spec.T], rtol=1e-12)
 
 
 def test_device_nmath_against_oracle_nmath(built_lib):
