@@ -83,6 +83,8 @@ struct McmcState {
   double* rec_theta;  // [n_chains][n_rec_rungs][rows_cap][d]
   double* rec_ll;     // [n_chains][n_rec_rungs][rows_cap]
   double* rec_lp;
+  // cached evaluation state of every particle's current parameter vector (layout: sweep_cache_layout), zero = not built yet
+  double* cache;
 };
 
 }  // namespace ccdev

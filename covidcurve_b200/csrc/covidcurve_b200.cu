@@ -55,6 +55,9 @@ constexpr int kWarpsPerCta = 4;
 #ifndef CC_MIN_CTAS
 #define CC_MIN_CTAS 4  // resident CTAs per SM the evaluation kernels are compiled for (caps registers at 128 per thread)
 #endif
+#ifndef CC_SWEEP_CTAS
+#define CC_SWEEP_CTAS 3  // resident 4-warp CTAs per SM the cached Metropolis sweep is compiled for (caps registers at 168)
+#endif
 #ifndef CC_P2_CTAS
 #define CC_P2_CTAS CC_MIN_CTAS  // the same for pass C of the batched likelihood alone (developer experiments)
 #endif
@@ -212,25 +215,42 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_init_tile
   }
 }
 
-// ---- per-warp shared memory of the cached Metropolis sweep: current and proposed copies of the record and of every
-// per-day array, so that a single-parameter proposal recomputes only the stages it touches and a rejection costs nothing
+// ---- the cached Metropolis sweep.
+// The cached state of a particle - its record and every per-day array of its CURRENT parameter vector - lives in global
+// memory (s.cache, ~13 kB per particle at the cfg3 shape: L2-resident for thousands of particles) and persists from one
+// iteration to the next.  Shared memory holds only the working set of the proposal in flight: the two records and ONE
+// buffer per array kind, filled either by recomputing the stage the proposed parameter touches or by loading the cached
+// array a dependent stage needs.  An accepted proposal writes the arrays it changed back; a rejected one costs nothing.
+// (The first version double-buffered all arrays in shared memory - 28 kB per warp, 8 warps per SM, and one full
+// re-evaluation per particle and sweep; this layout needs 14.6 kB per warp: 12 warps per SM.)
 struct SweepSmem {
-  double *recA, *recB, *xsA, *xsB, *gsA, *gsB, *aucA, *aucB, *skA, *skB, *ctab, *pcur, *pterm;
+  double *recA, *recB, *xs, *gs, *auc, *sk, *pcur, *pterm;
 };
-__host__ __device__ inline size_t sweep_smem_doubles(int d, int K, int A, int S, int NT) {
+struct SweepCacheLayout {
+  int rec, xs, gs, auc, sk, scal, size;  // offsets (doubles) into a particle's cache block; scal: tot, s1, sa_obs, s_all_auc, s_unc, irregular, valid
+  int nxs, ngs, nauc, nsk, nrec;
+};
+__host__ __device__ inline SweepCacheLayout sweep_cache_layout(int K, int A, int S, int NT) {
   const RecLayout L = rec_layout(K, A, S);
-  const size_t F = (size_t)((L.F + 3) & ~3), dp = (size_t)((d + 3) & ~3);
-  return 2 * F + 2 * (size_t)(12 * (8 * NT + 7)) + 2 * (size_t)(64 * NT + 16) + 2 * (size_t)(64 * NT) + 2 * (size_t)(64 * NT + 4) + 128 + dp + dp + 4;
+  SweepCacheLayout c;
+  c.nrec = (L.F + 3) & ~3; c.nxs = 12 * (8 * NT + 7); c.ngs = 64 * NT + 16; c.nauc = 64 * NT; c.nsk = 64 * NT + 4;
+  c.rec = 0; c.xs = c.rec + c.nrec; c.gs = c.xs + c.nxs; c.auc = c.gs + c.ngs; c.sk = c.auc + c.nauc; c.scal = c.sk + c.nsk;
+  c.size = c.scal + 8;
+  return c;
 }
-__device__ inline SweepSmem carve_sweep(double* q, int d, const RecLayout& L, int NT) {
+__host__ __device__ inline size_t sweep_smem_doubles(int d, int K, int A, int S, int NT) {
+  const SweepCacheLayout c = sweep_cache_layout(K, A, S, NT);
+  const size_t dp = (size_t)((d + 3) & ~3);
+  return 2 * (size_t)c.nrec + c.nxs + c.ngs + c.nauc + c.nsk + dp + dp + 4;
+}
+__device__ inline SweepSmem carve_sweep(double* q, int d, const SweepCacheLayout& c) {
   SweepSmem w;
-  const int F = (L.F + 3) & ~3, dp = (d + 3) & ~3;
-  w.recA = q; q += F; w.recB = q; q += F;
-  w.xsA = q; q += 12 * (8 * NT + 7); w.xsB = q; q += 12 * (8 * NT + 7);
-  w.gsA = q; q += 64 * NT + 16; w.gsB = q; q += 64 * NT + 16;
-  w.aucA = q; q += 64 * NT; w.aucB = q; q += 64 * NT;
-  w.skA = q; q += 64 * NT + 4; w.skB = q; q += 64 * NT + 4;
-  w.ctab = q; q += 128;
+  const int dp = (d + 3) & ~3;
+  w.recA = q; q += c.nrec; w.recB = q; q += c.nrec;
+  w.xs = q; q += c.nxs;
+  w.gs = q; q += c.ngs;
+  w.auc = q; q += c.nauc;
+  w.sk = q; q += c.nsk;
   w.pcur = q; q += dp;
   w.pterm = q;
   return w;
@@ -241,36 +261,51 @@ enum : int { kDepWeights = 1, kDepSpline = 2, kDepGamma = 4, kDepSero = 8 };
 template <typename T>
 __device__ __forceinline__ void swap_ptr(T*& a, T*& b) { T* t = a; a = b; b = t; }
 
+// warp-wide copy of n doubles (both sides 8-byte aligned; global side coalesced)
+// (no __restrict__ / const on purpose: the cache block is read back by the thread that wrote it within one kernel, so the
+// loads must stay on the coherent path)
+__device__ __forceinline__ void warp_copy(double* dst, double* src, int n) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int j = lane; j < n; j += 32) dst[j] = src[j];
+}
+
 // One sweep of d single-site Metropolis-Hastings updates for every (chain, rung); one warp per particle, walking particles.
-// Every per-day array of the particle's current state stays in shared memory across the d sub-steps; a proposal for
-// parameter i redoes only the stages that depend on it (m.dep[i]): the IFR / attack-rate / test parameters touch no
-// per-day stage at all, the knots skip the gamma table, mod/sod skip the spline, the seroconversion rate skips both.
-// Every cached quantity is a pure function of the current parameter vector, so the values equal a from-scratch evaluation.
-// `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
+// A proposal for parameter i redoes only the stages that depend on it (m.dep[i]): the IFR / attack-rate / test parameters
+// touch no per-day stage at all, the knots skip the gamma table, mod/sod skip the spline, the seroconversion rate skips
+// both.  Every cached quantity is a pure function of the current parameter vector, so the values equal a from-scratch
+// evaluation.  `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(const KModel m, const McmcState s, int iteration) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_cached_kernel(const KModel m, const McmcState s, int iteration) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
+  const SweepCacheLayout CL = sweep_cache_layout(m.K, m.A, m.S, NT);
   const int d = m.d;
-  SweepSmem w = carve_sweep(reinterpret_cast<double*>(smem_raw) + (size_t)warp * sweep_smem_doubles(d, m.K, m.A, m.S, NT), d, L, NT);
+  SweepSmem w = carve_sweep(reinterpret_cast<double*>(smem_raw) + (size_t)warp * sweep_smem_doubles(d, m.K, m.A, m.S, NT), d, CL);
   const TileTables tb = tile_tables_load(m, nullptr);
-  for (int i = lane; i < kXsLead; i += 32) w.xsA[i] = w.xsB[i] = 0.0;
-  if (lane < 7) w.gsA[lane] = w.gsB[lane] = 0.0;
+  for (int i = lane; i < kXsLead; i += 32) w.xs[i] = 0.0;  // the zeros in front of the series and of the delay kernel are
+  if (lane < 7) w.gs[lane] = 0.0;                          // never overwritten (full-array copies carry them along)
   __syncwarp();
   const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
   const int P = s.n_chains * s.rungs;
   const bool adapt = s.adapt_in_sampling || iteration <= s.burnin;
-  auto view = [&](double* rec, double* xs, double* gs, double* auc, double* sk) {
+  // tile_gamma keeps its coefficient table in the (not yet written) convolution output buffer and its reciprocal table
+  // behind the zero blocks of the series buffer
+  auto view = [&](double* rec) {
     TileSmem v;
-    v.rec = rec; v.xs = xs; v.gs = gs; v.auc = auc; v.sk = sk; v.ctab = w.ctab;
+    v.rec = rec; v.xs = w.xs; v.gs = w.gs; v.auc = w.auc; v.sk = w.sk; v.ctab = w.auc;
     return v;
   };
   // Poisson term from the cached sums (or day by day when they do not apply), written into `rec`
+  auto l1_needs_days = [&](const double* rec, const L1Sums& q) {
+    const double snm = rec[L.snm];
+    return q.irregular || !(snm > 0.0) || !isfinite(snm);
+  };
   auto finish_l1 = [&](double* rec, const L1Sums& q, const double* aucs) {
     const double snm = rec[L.snm];
     double l1, texpd;
-    if (!q.irregular && snm > 0.0 && isfinite(snm)) {
+    if (!l1_needs_days(rec, q)) {
       l1 = (q.s1 + m.l1_sumx * log(snm)) - snm * q.sa_obs;
       texpd = snm * q.s_all_auc;
     } else {
@@ -297,42 +332,64 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(co
     double* bw = s.bw + (size_t)slot * d;
     int* bwi = s.bw_index + (size_t)slot * d;
     unsigned int* macc = s.move_acc + (size_t)b * d;
+    double* cache = s.cache + (size_t)p * CL.size;
     double ll = s.ll[p], lp = s.lp[p];
 
-    // ---- rebuild the caches of the current state (one full evaluation per particle and sweep)
     __syncwarp();
     for (int j = lane; j < d; j += 32) w.pcur[j] = th[j];
     __syncwarp();
     for (int j = lane; j < d; j += 32) w.pterm[j] = prior_term(m, j, w.pcur[j]);
     if (lane < 3) w.pterm[d + lane] = (m.jac_rows[lane] >= 0) ? m.jac_counts[lane] * log(w.pcur[max(m.jac_rows[lane], 0)]) : 0.0;
-    if (lane == 0) {
-      auto parc = [&](int j) { return w.pcur[j]; };
-      auto putA = [&](int f, double v) { w.recA[f] = v; };
-      w.recA[L.o_status] = 0.0;
-      p1_weights(m, L, parc, putA);
-      if (p1_spline(m, L, parc, putA)) {
-        p1_gamma<NT>(m, L, parc, putA);
-        p1_sero(m, L, parc, putA);
-      }
-    }
-    __syncwarp();
     double tot_cur = 0.0;
     L1Sums sums_cur = {0.0, 0.0, 0.0, 0.0, 1};
-    if (w.recA[L.flags] != 0.0) {
-      tile_sero_prefix<NT>(m, L, view(w.recA, w.xsB, w.gsB, w.aucB, w.skA), tb);
-      tile_gamma<NT>(m, L, view(w.recA, w.xsB, w.gsA, w.aucB, w.skA), tb);
-      tot_cur = stage_spline<NT>(m, L, w.recA, w.xsA);
-      const bool ok = stage_popn(m, L, w.recA, tot_cur);
-      if (lane == 0) w.recA[L.o_status] = ok ? 0.0 : 1.0;
+    if (cache[CL.scal + 6] != 0.0) {
+      // caches of the current state, left by the previous sweep
+      warp_copy(w.recA, cache + CL.rec, CL.nrec);
+      tot_cur = cache[CL.scal + 0];
+      sums_cur.s1 = cache[CL.scal + 1]; sums_cur.sa_obs = cache[CL.scal + 2]; sums_cur.s_all_auc = cache[CL.scal + 3];
+      sums_cur.s_unc = cache[CL.scal + 4]; sums_cur.irregular = (int)cache[CL.scal + 5];
       __syncwarp();
-      if (ok) {
-        stage_conv<NT>(m, w.xsA, w.gsA, w.aucA);
-        sums_cur = stage_l1_sums(m, tb, w.aucA);
-        stage_surveys(m, w.xsA, w.skA, [&](int sv, double v) { w.recA[L.o_base + sv] = v; });
-        finish_l1(w.recA, sums_cur, w.aucA);
+    } else {
+      // first sweep: one full evaluation builds them
+      if (lane == 0) {
+        auto parc = [&](int j) { return w.pcur[j]; };
+        auto putA = [&](int f, double v) { w.recA[f] = v; };
+        w.recA[L.o_status] = 0.0;
+        p1_weights(m, L, parc, putA);
+        if (p1_spline(m, L, parc, putA)) {
+          p1_gamma<NT>(m, L, parc, putA);
+          p1_sero(m, L, parc, putA);
+        }
       }
+      __syncwarp();
+      if (w.recA[L.flags] != 0.0) {
+        tile_sero_prefix<NT>(m, L, view(w.recA), tb);
+        tile_gamma<NT>(m, L, view(w.recA), tb);
+        tot_cur = stage_spline<NT>(m, L, w.recA, w.xs);
+        const bool ok = stage_popn(m, L, w.recA, tot_cur);
+        if (lane == 0) w.recA[L.o_status] = ok ? 0.0 : 1.0;
+        __syncwarp();
+        if (ok) {
+          stage_conv<NT>(m, w.xs, w.gs, w.auc);
+          sums_cur = stage_l1_sums(m, tb, w.auc);
+          stage_surveys(m, w.xs, w.sk, [&](int sv, double v) { w.recA[L.o_base + sv] = v; });
+          finish_l1(w.recA, sums_cur, w.auc);
+        }
+        warp_copy(cache + CL.xs + kXsLead, w.xs + kXsLead, CL.nxs - kXsLead);
+        warp_copy(cache + CL.gs, w.gs, CL.ngs);
+        warp_copy(cache + CL.auc, w.auc, CL.nauc);
+        warp_copy(cache + CL.sk, w.sk, CL.nsk);
+      }
+      __syncwarp();
+      warp_copy(cache + CL.rec, w.recA, CL.nrec);
+      if (lane == 0) {
+        cache[CL.scal + 0] = tot_cur;
+        cache[CL.scal + 1] = sums_cur.s1; cache[CL.scal + 2] = sums_cur.sa_obs; cache[CL.scal + 3] = sums_cur.s_all_auc;
+        cache[CL.scal + 4] = sums_cur.s_unc; cache[CL.scal + 5] = (double)sums_cur.irregular;
+        cache[CL.scal + 6] = 1.0;
+      }
+      __syncwarp();
     }
-    __syncwarp();
 
     for (int i = 0; i < d; i++) {
       const int dep = m.dep[i];
@@ -366,24 +423,42 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(co
       const bool do_sero = valid && ((dep & kDepSero) || from_invalid);
       const bool do_gamma = valid && ((dep & kDepGamma) || from_invalid);
       const bool do_spline = valid && ((dep & kDepSpline) || from_invalid);
-      double* use_xs = w.xsA; double* use_gs = w.gsA; double* use_auc = w.aucA; double* use_sk = w.skA;
+      const bool need_conv = do_spline || do_gamma, need_surv = do_spline || do_sero;
+      bool new_auc = false;
       double tot_p = tot_cur;
       L1Sums sums_p = sums_cur;
       if (valid) {
-        if (do_sero) { tile_sero_prefix<NT>(m, L, view(w.recB, w.xsB, w.gsB, w.aucB, w.skB), tb); use_sk = w.skB; }
-        if (do_gamma) { tile_gamma<NT>(m, L, view(w.recB, w.xsB, w.gsB, w.aucB, w.skB), tb); use_gs = w.gsB; }
-        if (do_spline) { tot_p = stage_spline<NT>(m, L, w.recB, w.xsB); use_xs = w.xsB; }
+        // stage order: the hazard convolution of the seroreversion model borrows the series and kernel buffers, and the
+        // gamma table uses the series buffer as scratch, so both run before the series is produced or fetched
+        if (do_sero) tile_sero_prefix<NT>(m, L, view(w.recB), tb);
+        if (do_gamma) tile_gamma<NT>(m, L, view(w.recB), tb);
+        if (do_spline) tot_p = stage_spline<NT>(m, L, w.recB, w.xs);
+        else if (need_conv || need_surv) warp_copy(w.xs + kXsLead, cache + CL.xs + kXsLead, CL.nxs - kXsLead);
         const bool ok = stage_popn(m, L, w.recB, tot_p);
         if (lane == 0) w.recB[L.o_status] = ok ? 0.0 : 1.0;
         __syncwarp();
         if (ok) {
-          if (do_spline || do_gamma) {
-            stage_conv<NT>(m, use_xs, use_gs, w.aucB);
-            use_auc = w.aucB;
-            sums_p = stage_l1_sums(m, tb, w.aucB);
+          if (need_conv) {
+            if (!do_gamma) {
+              warp_copy(w.gs, cache + CL.gs, CL.ngs);
+              __syncwarp();
+            }
+            stage_conv<NT>(m, w.xs, w.gs, w.auc);
+            new_auc = true;
+            sums_p = stage_l1_sums(m, tb, w.auc);
           }
-          if (do_spline || do_sero) stage_surveys(m, use_xs, use_sk, [&](int sv, double v) { w.recB[L.o_base + sv] = v; });
-          finish_l1(w.recB, sums_p, use_auc);
+          if (need_surv) {
+            if (!do_sero) {
+              warp_copy(w.sk, cache + CL.sk, CL.nsk);
+              __syncwarp();
+            }
+            stage_surveys(m, w.xs, w.sk, [&](int sv, double v) { w.recB[L.o_base + sv] = v; });
+          }
+          if (!new_auc && l1_needs_days(w.recB, sums_p)) {  // rare: the day-by-day Poisson term needs the cached convolution
+            warp_copy(w.auc, cache + CL.auc, CL.nauc);
+            __syncwarp();
+          }
+          finish_l1(w.recB, sums_p, w.auc);
         }
       }
       __syncwarp();
@@ -400,7 +475,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(co
         if (lane < 3 && m.jac_rows[lane] >= 0) v += (lane == 0) ? jac_new[0] : (lane == 1) ? jac_new[1] : jac_new[2];
         v = warp_sum(v);
         if (!isfinite(v)) v = -CC_OVERFLO;
-        pt_new = pt_new;  // (kept for the commit below)
         const double lpp = v;
         const double mh = beta * (llp - ll) + (lpp - lp) + adj;
         const bool acc = log(dr.u) < mh;  // warp-uniform
@@ -408,14 +482,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) mcmc_sweep_cached_kernel(co
         if (acc) {
           ll = llp;
           lp = lpp;
+          // commit: the proposal's record and the arrays it recomputed become the cached state
+          warp_copy(cache + CL.rec, w.recB, CL.nrec);
+          if (do_spline) warp_copy(cache + CL.xs + kXsLead, w.xs + kXsLead, CL.nxs - kXsLead);
+          if (do_gamma) warp_copy(cache + CL.gs, w.gs, CL.ngs);
+          if (new_auc) warp_copy(cache + CL.auc, w.auc, CL.nauc);
+          if (do_sero) warp_copy(cache + CL.sk, w.sk, CL.nsk);
           swap_ptr(w.recA, w.recB);
-          if (use_xs == w.xsB) swap_ptr(w.xsA, w.xsB);
-          if (use_gs == w.gsB) swap_ptr(w.gsA, w.gsB);
-          if (use_auc == w.aucB) swap_ptr(w.aucA, w.aucB);
-          if (use_sk == w.skB) swap_ptr(w.skA, w.skB);
           tot_cur = tot_p;
           sums_cur = sums_p;
           if (lane == 0) {
+            cache[CL.scal + 0] = tot_cur;
+            cache[CL.scal + 1] = sums_cur.s1; cache[CL.scal + 2] = sums_cur.sa_obs; cache[CL.scal + 3] = sums_cur.s_all_auc;
+            cache[CL.scal + 4] = sums_cur.s_unc; cache[CL.scal + 5] = (double)sums_cur.irregular;
             w.pcur[i] = thp;
             w.pterm[i] = pt_new;
             for (int j = 0; j < 3; j++) w.pterm[d + j] = jac_new[j];
@@ -953,26 +1032,35 @@ typedef int (*launch_fn)(cc_model*, const double*, long long, long long, double*
 // pageable memory still works (the driver stages it).
 static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long long n, long long ld, double* out) {
   const int d = m->k.d;
-  // at least ~4 chunks in flight for large batches (copy/compute overlap), chunks large enough to fill the GPU
-  long long chunk = ((n + 3) / 4 + 1023) & ~1023LL;
-  chunk = std::min<long long>(std::max<long long>(chunk, 1 << 16), 1 << 18);
-  chunk = std::min<long long>(n, chunk);
-  int rc = ensure_stage(m, (size_t)2 * d * chunk * sizeof(double), (size_t)2 * chunk * sizeof(double));
+  // Chunk sizes grow geometrically (64k, 128k, ... up to 512k vectors): only the first chunk's upload and the last
+  // chunk's download are exposed, so they are kept small, while the bulk runs in large launches (measured on B200 at
+  // 2^20 vectors: fixed 128k chunks 56.8 M evals/s, 256k 58.6, 512k 60.1; profiles/r1_summary.md)
+  long long cmax = 1 << 19;
+  if (const char* e = std::getenv("CC_HOST_CHUNK")) cmax = std::max<long long>(1024, (std::atoll(e) + 1023) & ~1023LL);  // developer tuning
+  cmax = std::min<long long>(cmax, (n + 1023) & ~1023LL);
+  int rc = ensure_stage(m, (size_t)2 * d * cmax * sizeof(double), (size_t)2 * cmax * sizeof(double));
   if (rc) return rc;
+  if (fn == launch_loglike)  // size both work slots for the largest chunk now: growing them mid-pipeline would synchronise the device
+    for (int slot = 1; slot <= 2; slot++)
+      if ((rc = ensure_work(m, slot, std::min(cmax, n)))) return rc;
   cudaStream_t st[2] = {m->stream, m->stream2};
   CC_CUDA(cudaEventRecord(m->ev0, st[0]));
   m->last_launches = 0;
   int q = 0;
-  for (long long c0 = 0; c0 < n; c0 += chunk, q ^= 1) {
-    const long long cn = std::min(chunk, n - c0);
-    double* dth = m->d_stage + (size_t)q * d * chunk;
-    double* dout = m->d_out + (size_t)q * chunk;
-    CC_CUDA(cudaMemcpy2DAsync(dth, (size_t)chunk * sizeof(double), theta + c0, (size_t)ld * sizeof(double),
+  long long chunk = std::min<long long>(cmax, 1 << 16);
+  for (long long c0 = 0; c0 < n; q ^= 1) {
+    long long cn = std::min(chunk, n - c0);
+    if (n - c0 - cn < (1 << 15)) cn = std::min(n - c0, cmax);  // do not leave a sliver behind
+    double* dth = m->d_stage + (size_t)q * d * cmax;
+    double* dout = m->d_out + (size_t)q * cmax;
+    CC_CUDA(cudaMemcpy2DAsync(dth, (size_t)cmax * sizeof(double), theta + c0, (size_t)ld * sizeof(double),
                               (size_t)cn * sizeof(double), (size_t)d, cudaMemcpyHostToDevice, st[q]));
-    rc = fn(m, dth, cn, chunk, dout, st[q], 1 + q);
+    rc = fn(m, dth, cn, cmax, dout, st[q], 1 + q);
     if (rc) return rc;
     m->last_launches += 5;
     CC_CUDA(cudaMemcpyAsync(out + c0, dout, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost, st[q]));
+    c0 += cn;
+    chunk = std::min<long long>(2 * chunk, cmax);
   }
   CC_CUDA(cudaEventRecord(m->ev_stage[1], st[1]));
   CC_CUDA(cudaStreamWaitEvent(st[0], m->ev_stage[1], 0));
@@ -1171,7 +1259,8 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
       (rc = dalloc(r, &s.move_acc, P * d)) || (rc = dalloc(r, &s.at_rung, P)) || (rc = dalloc(r, &s.beta, (size_t)R)) ||
       (rc = dalloc(r, &s.swap_acc, (size_t)C * std::max(R - 1, 1))) || (rc = dalloc(r, &s.swap_try, (size_t)C * std::max(R - 1, 1))) ||
       (rc = dalloc(r, &s.rec_theta, rec * d, false)) || (rc = dalloc(r, &s.rec_ll, rec, false)) ||
-      (rc = dalloc(r, &s.rec_lp, rec, false))) {
+      (rc = dalloc(r, &s.rec_lp, rec, false)) ||
+      (rc = dalloc(r, &s.cache, P * (size_t)sweep_cache_layout(m->k.K, m->k.A, m->k.S, m->nt).size))) {
     cc_mcmc_destroy(r);
     return rc;
   }
@@ -1204,22 +1293,32 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
     const long long tiles = ((long long)P + (1 << le) - 1) >> le;
     r->grid = (unsigned)std::min<long long>((tiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)m->grid_max);
     {
+      // warps per CTA and CTAs per SM of the sweep: whatever keeps the most warps resident (shared memory and registers)
       const size_t per_warp = sweep_smem_doubles(d, m->k.K, m->k.A, m->k.S, m->nt) * sizeof(double);
-      const size_t cap = 227 * 1024;
-      int best_wpc = 0, best_warps = 0;
+      int best_wpc = 0, best_warps = 0, best_ctas = 0;
       for (int wpc = kWarpsPerCta; wpc >= 1; wpc >>= 1) {
-        const int ctas = (int)(cap / (per_warp * wpc));
-        const int warps = std::min(ctas * wpc, 16);
-        if (warps > best_warps) { best_warps = warps; best_wpc = wpc; }
+        int ctas = 0;
+        cudaError_t oe = cudaSuccess;
+        switch (m->nt) {
+#define CC_OCC(NT_) case NT_: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, mcmc_sweep_cached_kernel<NT_>, 32 * wpc, per_warp * wpc); break;
+          CC_FOR_EACH_NT(CC_OCC)
+#undef CC_OCC
+          default: break;
+        }
+        if (oe != cudaSuccess) ctas = 0;
+        if (ctas * wpc > best_warps) { best_warps = ctas * wpc; best_wpc = wpc; best_ctas = ctas; }
       }
       if (best_wpc == 0) {
+        cudaGetLastError();
         cc_mcmc_destroy(r);
         return fail(CC_E_INVALID, "model too large for the shared memory of the Metropolis sweep kernel");
       }
       r->sweep_wpc = best_wpc;
       r->sweep_smem = per_warp * best_wpc;
-      const long long ctas_per_sm = std::max<long long>(1, (long long)(cap / r->sweep_smem));
-      r->sweep_grid = (unsigned)std::min<long long>(((long long)P + best_wpc - 1) / best_wpc, ctas_per_sm * m->sm_count);
+      r->sweep_grid = (unsigned)std::min<long long>(((long long)P + best_wpc - 1) / best_wpc, (long long)best_ctas * m->sm_count);
+      if (std::getenv("CC_VERBOSE"))
+        std::fprintf(stderr, "covidcurve_b200: sweep kernel %d warps/CTA x %d CTAs/SM, %zu B smem/CTA, grid %u, cache %.1f MB\n", best_wpc,
+                     best_ctas, r->sweep_smem, r->sweep_grid, (double)P * sweep_cache_layout(m->k.K, m->k.A, m->k.S, m->nt).size * 8e-6);
     }
     const RecLayout L = rec_layout(m->k.K, m->k.A, m->k.S);
     if ((rc = dalloc(r, &r->scratch, (size_t)r->grid * kWarpsPerCta * L.F * 32, false))) {
