@@ -90,6 +90,8 @@ __device__ inline void tile_smem_init(const TileSmem& w) {
 // single out-of-line copies of the heavy scalar routines (instruction footprint)
 __device__ __noinline__ double dbinom_log_shared(double x, double n, double p) { return dbinom_log(x, n, p); }
 __device__ __forceinline__ double lgamma_shared(double x) { return lgamma(x); }
+// the general incomplete-gamma algorithm is ~8 700 instructions and runs only for shapes outside the validated box
+__device__ __noinline__ double pgamma_lower_shared(const GammaShape& g, double x) { return pgamma_lower(g, x); }
 
 // ------------------------------------------------------------------------------------------------ phase 1
 // Scalar-per-vector pieces.  `par(i)` returns parameter i of the vector, `put(f, v)` stores record field f.
@@ -114,6 +116,33 @@ __device__ inline void p1_weights(const KModel& m, const RecLayout& L, Par par, 
   put(L.snm, snm);
   put(L.sens, par(m.idx_sens));
   put(L.spec, par(m.idx_spec));
+}
+
+// the same, by a whole warp on a record in shared memory: one stratum per lane for the divisions, the two sums in the
+// serial order of the scalar version (identical values)
+template <typename Par>
+__device__ inline void p1_weights_warp(const KModel& m, const RecLayout& L, Par par, double* rec) {
+  const int A = m.A, lane = threadIdx.x & 31;
+  double nedom = 0.0;
+  if (A > 1)
+    for (int a = 0; a < A; a++) nedom += par(m.idx_noise[a]) * (double)m.demog[a];
+  for (int a = lane; a < A; a += 32) {
+    const int r = m.idx_ifr[a];
+    double ma = par(r);
+    if (m.reparam_ifr && r != m.idx_max_ma) ma = ma * par(m.idx_max_ma);
+    const double ne = (A > 1) ? (par(m.idx_noise[a]) * (double)m.demog[a]) / nedom : (m.binomial ? 1.0 : 0.0);
+    rec[L.ne + a] = ne;
+    rec[L.nm + a] = ne * ma;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double snm = 0.0;
+    for (int a = 0; a < A; a++) snm += rec[L.nm + a];
+    rec[L.snm] = snm;
+    rec[L.sens] = par(m.idx_sens);
+    rec[L.spec] = par(m.idx_spec);
+  }
+  __syncwarp();
 }
 
 // role map with the re-parameterisation lift (Agecpp2strings.R:277-355), knot order (binomial.cpp:88-96), natural cubic
@@ -301,7 +330,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
     for (int k = lane; k <= T; k += 32) {
       double v;
       if (bad) v = (isnan(scale) || isnan(alph)) ? (scale + alph) : d_nan();
-      else v = pgamma_lower(gsh, (double)k / scale);
+      else v = pgamma_lower_shared(gsh, (double)k / scale);
       P[k] = v;
     }
   } else {
@@ -708,6 +737,15 @@ __device__ __forceinline__ double prior_term(const KModel& m, int i, double x) {
   if (fam == CC_PRIOR_NONE) return 0.0;
   const double a = m.prior_p1[i], b = m.prior_p2[i];
   return (fam == CC_PRIOR_DUNIF) ? dunif_log(x, a, b) : (fam == CC_PRIOR_DNORM) ? dnorm_log(x, a, b) : dbeta_log(x, a, b);
+}
+
+// out-of-line copy for the Metropolis sweep (the beta density alone is ~2 000 instructions)
+__device__ __noinline__ double prior_density_shared(int fam, double x, double a, double b) {
+  return (fam == CC_PRIOR_DUNIF) ? dunif_log(x, a, b) : (fam == CC_PRIOR_DNORM) ? dnorm_log(x, a, b) : dbeta_log(x, a, b);
+}
+__device__ __forceinline__ double prior_term_shared(const KModel& m, int i, double x) {
+  const int fam = m.prior_family[i];
+  return (fam == CC_PRIOR_NONE) ? 0.0 : prior_density_shared(fam, x, m.prior_p1[i], m.prior_p2[i]);
 }
 
 // generated logprior for E vectors per warp: G lanes per vector, terms strided over sub (Agecpp2strings.R:66-219)

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_init_tile
 // re-evaluation per particle and sweep; this layout needs 14.6 kB per warp: 12 warps per SM.)
 struct SweepSmem {
   double *recA, *recB, *xs, *gs, *auc, *sk, *pcur, *pterm;
+  double *q_thp, *q_php, *q_adj, *q_ptn, *q_logu;  // the sweep's d proposals, drawn up front (q_logu[i] becomes the accept flag)
 };
 struct SweepCacheLayout {
   int rec, xs, gs, auc, sk, scal, size;  // offsets (doubles) into a particle's cache block; scal: tot, s1, sa_obs, s_all_auc, s_unc, irregular, valid
@@ -241,7 +242,7 @@ __host__ __device__ inline SweepCacheLayout sweep_cache_layout(int K, int A, int
 __host__ __device__ inline size_t sweep_smem_doubles(int d, int K, int A, int S, int NT) {
   const SweepCacheLayout c = sweep_cache_layout(K, A, S, NT);
   const size_t dp = (size_t)((d + 3) & ~3);
-  return 2 * (size_t)c.nrec + c.nxs + c.ngs + c.nauc + c.nsk + dp + dp + 4;
+  return 2 * (size_t)c.nrec + c.nxs + c.ngs + c.nauc + c.nsk + dp + dp + 4 + 5 * dp;
 }
 __device__ inline SweepSmem carve_sweep(double* q, int d, const SweepCacheLayout& c) {
   SweepSmem w;
@@ -252,7 +253,8 @@ __device__ inline SweepSmem carve_sweep(double* q, int d, const SweepCacheLayout
   w.auc = q; q += c.nauc;
   w.sk = q; q += c.nsk;
   w.pcur = q; q += dp;
-  w.pterm = q;
+  w.pterm = q; q += dp + 4;
+  w.q_thp = q; q += dp; w.q_php = q; q += dp; w.q_adj = q; q += dp; w.q_ptn = q; q += dp; w.q_logu = q;
   return w;
 }
 
@@ -338,79 +340,53 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
     __syncwarp();
     for (int j = lane; j < d; j += 32) w.pcur[j] = th[j];
     __syncwarp();
-    for (int j = lane; j < d; j += 32) w.pterm[j] = prior_term(m, j, w.pcur[j]);
+    for (int j = lane; j < d; j += 32) w.pterm[j] = prior_term_shared(m, j, w.pcur[j]);
     if (lane < 3) w.pterm[d + lane] = (m.jac_rows[lane] >= 0) ? m.jac_counts[lane] * log(w.pcur[max(m.jac_rows[lane], 0)]) : 0.0;
+    // All d proposals of this sweep at once, one parameter per lane: parameter i's random numbers are keyed by (chain,
+    // particle, iteration, i), and phi[i], bw[i] and theta[i] are touched by update i alone, so drawing them ahead of the
+    // sequential accept/reject loop changes no value - it only takes the Philox rounds, the transforms, the proposed
+    // prior term and log(u) off the per-update dependency chain.
+    for (int j = lane; j < d; j += 32) {
+      const ccrng::Draw dr = ccrng::draw(s.seed, ccrng::kStreamMove, (uint32_t)(s.chain_offset + c), (uint32_t)pid,
+                                         (uint32_t)iteration, (uint32_t)j);
+      const double lo = m.pmin[j], hi = m.pmax[j];
+      const int tt = trans_type(lo, hi);
+      const double php = ph[j] + bw[j] * dr.z;
+      const double thp = phi_to_theta(tt, php, lo, hi);
+      w.q_php[j] = php;
+      w.q_thp[j] = thp;
+      w.q_adj[j] = mh_adjust(tt, w.pcur[j], thp, lo, hi);
+      w.q_ptn[j] = prior_term_shared(m, j, thp);
+      w.q_logu[j] = log(dr.u);
+    }
+    __syncwarp();
     double tot_cur = 0.0;
     L1Sums sums_cur = {0.0, 0.0, 0.0, 0.0, 1};
-    if (cache[CL.scal + 6] != 0.0) {
+    bool unbuilt = cache[CL.scal + 6] == 0.0;
+    if (!unbuilt) {
       // caches of the current state, left by the previous sweep
       warp_copy(w.recA, cache + CL.rec, CL.nrec);
       tot_cur = cache[CL.scal + 0];
       sums_cur.s1 = cache[CL.scal + 1]; sums_cur.sa_obs = cache[CL.scal + 2]; sums_cur.s_all_auc = cache[CL.scal + 3];
       sums_cur.s_unc = cache[CL.scal + 4]; sums_cur.irregular = (int)cache[CL.scal + 5];
-      __syncwarp();
     } else {
-      // first sweep: one full evaluation builds them
-      if (lane == 0) {
-        auto parc = [&](int j) { return w.pcur[j]; };
-        auto putA = [&](int f, double v) { w.recA[f] = v; };
-        w.recA[L.o_status] = 0.0;
-        p1_weights(m, L, parc, putA);
-        if (p1_spline(m, L, parc, putA)) {
-          p1_gamma<NT>(m, L, parc, putA);
-          p1_sero(m, L, parc, putA);
-        }
-      }
-      __syncwarp();
-      if (w.recA[L.flags] != 0.0) {
-        tile_sero_prefix<NT>(m, L, view(w.recA), tb);
-        tile_gamma<NT>(m, L, view(w.recA), tb);
-        tot_cur = stage_spline<NT>(m, L, w.recA, w.xs);
-        const bool ok = stage_popn(m, L, w.recA, tot_cur);
-        if (lane == 0) w.recA[L.o_status] = ok ? 0.0 : 1.0;
-        __syncwarp();
-        if (ok) {
-          stage_conv<NT>(m, w.xs, w.gs, w.auc);
-          sums_cur = stage_l1_sums(m, tb, w.auc);
-          stage_surveys(m, w.xs, w.sk, [&](int sv, double v) { w.recA[L.o_base + sv] = v; });
-          finish_l1(w.recA, sums_cur, w.auc);
-        }
-        warp_copy(cache + CL.xs + kXsLead, w.xs + kXsLead, CL.nxs - kXsLead);
-        warp_copy(cache + CL.gs, w.gs, CL.ngs);
-        warp_copy(cache + CL.auc, w.auc, CL.nauc);
-        warp_copy(cache + CL.sk, w.sk, CL.nsk);
-      }
-      __syncwarp();
-      warp_copy(cache + CL.rec, w.recA, CL.nrec);
-      if (lane == 0) {
-        cache[CL.scal + 0] = tot_cur;
-        cache[CL.scal + 1] = sums_cur.s1; cache[CL.scal + 2] = sums_cur.sa_obs; cache[CL.scal + 3] = sums_cur.s_all_auc;
-        cache[CL.scal + 4] = sums_cur.s_unc; cache[CL.scal + 5] = (double)sums_cur.irregular;
-        cache[CL.scal + 6] = 1.0;
-      }
-      __syncwarp();
+      // First sweep of a particle: nothing is cached yet.  An all-zero record reads as "no usable caches" (flags == 0), so
+      // every proposal is evaluated from scratch until the first one is accepted and becomes the cached state.
+      for (int f = lane; f < CL.nrec; f += 32) w.recA[f] = 0.0;
     }
+    __syncwarp();
 
     for (int i = 0; i < d; i++) {
       const int dep = m.dep[i];
-      // every lane computes the (cheap) proposal redundantly
-      const ccrng::Draw dr = ccrng::draw(s.seed, ccrng::kStreamMove, (uint32_t)(s.chain_offset + c), (uint32_t)pid,
-                                         (uint32_t)iteration, (uint32_t)i);
-      const double lo = m.pmin[i], hi = m.pmax[i];
-      const int tt = trans_type(lo, hi);
-      const double th_old = w.pcur[i];
-      const double bwv = bw[i];
-      const double php = ph[i] + bwv * dr.z;
-      const double thp = phi_to_theta(tt, php, lo, hi);
-      const double adj = mh_adjust(tt, th_old, thp, lo, hi);
+      const double thp = w.q_thp[i], php = w.q_php[i], adj = w.q_adj[i];
       auto par = [&](int j) { return j == i ? thp : w.pcur[j]; };
       for (int f = lane; f < L.F; f += 32) w.recB[f] = w.recA[f];
       __syncwarp();
+      if ((dep & kDepWeights) || unbuilt) p1_weights_warp(m, L, par, w.recB);
       if (lane == 0) {
         auto putB = [&](int f, double v) { w.recB[f] = v; };
-        if (dep & kDepWeights) p1_weights(m, L, par, putB);
         bool ok = w.recB[L.flags] != 0.0;
-        if (dep & kDepSpline) ok = p1_spline(m, L, par, putB);
+        if ((dep & kDepSpline) || unbuilt) ok = p1_spline(m, L, par, putB);
         // a vector whose knots were disordered has no gamma / sero constants yet: build them when the knots come back
         const bool need_all = ok && (w.recA[L.flags] == 0.0);
         if (ok && ((dep & kDepGamma) || need_all)) p1_gamma<NT>(m, L, par, putB);
@@ -466,7 +442,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
       // prior: only term i (and a Jacobian term if i is a reference parameter) changes
       double pt_new = 0.0, jac_new[3] = {0.0, 0.0, 0.0};
       {
-        pt_new = prior_term(m, i, thp);
+        pt_new = w.q_ptn[i];
 #pragma unroll
         for (int j = 0; j < 3; j++) jac_new[j] = (m.jac_rows[j] == i) ? m.jac_counts[j] * log(thp) : w.pterm[d + j];
         double v = 0.0;
@@ -477,7 +453,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
         if (!isfinite(v)) v = -CC_OVERFLO;
         const double lpp = v;
         const double mh = beta * (llp - ll) + (lpp - lp) + adj;
-        const bool acc = log(dr.u) < mh;  // warp-uniform
+        const bool acc = w.q_logu[i] < mh;  // warp-uniform
         __syncwarp();
         if (acc) {
           ll = llp;
@@ -489,12 +465,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
           if (new_auc) warp_copy(cache + CL.auc, w.auc, CL.nauc);
           if (do_sero) warp_copy(cache + CL.sk, w.sk, CL.nsk);
           swap_ptr(w.recA, w.recB);
+          unbuilt = false;
           tot_cur = tot_p;
           sums_cur = sums_p;
           if (lane == 0) {
             cache[CL.scal + 0] = tot_cur;
             cache[CL.scal + 1] = sums_cur.s1; cache[CL.scal + 2] = sums_cur.sa_obs; cache[CL.scal + 3] = sums_cur.s_all_auc;
             cache[CL.scal + 4] = sums_cur.s_unc; cache[CL.scal + 5] = (double)sums_cur.irregular;
+            cache[CL.scal + 6] = 1.0;
             w.pcur[i] = thp;
             w.pterm[i] = pt_new;
             for (int j = 0; j < 3; j++) w.pterm[d + j] = jac_new[j];
@@ -503,13 +481,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
             macc[i] += 1u;
           }
         }
-        if (lane == 0 && adapt) {
-          // Robbins-Monro on log(bw) towards a 0.234 acceptance rate
-          const double step = acc ? (1.0 - 0.234) : -0.234;
-          bw[i] = bwv * exp(step / sqrt((double)bwi[i]));  // = exp(log bw + step / sqrt(n))
-          bwi[i] += 1;
-        }
         __syncwarp();
+        if (lane == 0) w.q_logu[i] = acc ? 1.0 : 0.0;  // remembered for the bandwidth update below
+        __syncwarp();
+      }
+    }
+    if (adapt) {
+      // Robbins-Monro on log(bw) towards a 0.234 acceptance rate, one parameter per lane
+      __syncwarp();
+      for (int j = lane; j < d; j += 32) {
+        const double step = (w.q_logu[j] != 0.0) ? (1.0 - 0.234) : -0.234;
+        bw[j] = bw[j] * exp(step / sqrt((double)bwi[j]));  // = exp(log bw + step / sqrt(n))
+        bwi[j] += 1;
       }
     }
     if (lane == 0) {
