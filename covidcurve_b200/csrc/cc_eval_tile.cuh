@@ -541,11 +541,25 @@ __device__ inline bool stage_popn(const KModel& m, const RecLayout& L, const dou
 }
 
 // ---- S7 death-delay convolution on the tensor cores, then back to day order through shared memory
+// Number of 8-day lag blocks of the delay kernel that can be non-zero.  Beyond x = alph + 9 sqrt(alph) + 45 the upper tail
+// is below 2^-54, every P value rounds to exactly 1 (in R as here) and the kernel masses are exactly zero, so the lag blocks
+// out there are skipped without changing a bit (short delays: most of the triangle for sod < 0.5).
+__device__ inline int conv_lag_blocks(const KModel& m, const RecLayout& L, const double* rec) {
+  const int nb = (m.T + 7) >> 3;
+  const double alph = rec[L.gam + 0], scale = rec[L.gam + 1];
+  if (rec[L.gam + 8] == 0.0 || !(alph > 0.0) || !(scale > 0.0)) return nb;  // general algorithm: keep everything
+  const double k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;
+  if (!(k_hi < (double)m.T)) return nb;
+  const int kend = (int)k_hi + 2;                     // first day whose mass is exactly zero (tile_gamma)
+  return min(nb, ((kend + 14) >> 3) + 1);            // block dl holds lags 8 dl - 7 .. 8 dl + 7
+}
+
 template <int NT>
-__device__ inline void stage_conv(const KModel& m, const double* __restrict__ xs, const double* __restrict__ gs, double* aucs) {
+__device__ inline void stage_conv(const KModel& m, const double* __restrict__ xs, const double* __restrict__ gs, double* aucs, int nb) {
   const int lane = threadIdx.x & 31;
   double auc[NT][2];
-  toeplitz_dmma<NT>(xs, gs, (m.T + 7) >> 3, auc);
+  nb = __shfl_sync(0xffffffffu, nb, 0);  // warp-uniform by construction; tell the compiler so (uniform loop exits around the MMAs)
+  toeplitz_dmma<NT>(xs, gs, nb, auc);
   __syncwarp();  // aucs may alias the kernel region
   const int n = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -664,7 +678,7 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   __syncwarp();
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
     for (int j = lane; j < T; j += 32) m.debug_dump[j] = w.gs[7 + j];
-  stage_conv<NT>(m, w.xs, w.gs, w.auc);
+  stage_conv<NT>(m, w.xs, w.gs, w.auc, conv_lag_blocks(m, L, w.rec));
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
     for (int j = lane; j < T; j += 32) {
       m.debug_dump[T + j] = w.xs[xs_index(j)];

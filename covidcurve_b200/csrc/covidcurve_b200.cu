@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
               warp_copy(w.gs, cache + CL.gs, CL.ngs);
               __syncwarp();
             }
-            stage_conv<NT>(m, w.xs, w.gs, w.auc);
+            stage_conv<NT>(m, w.xs, w.gs, w.auc, conv_lag_blocks(m, L, w.recB));
             new_auc = true;
             sums_p = stage_l1_sums(m, tb, w.auc);
           }
