@@ -77,6 +77,8 @@ SYMBOLS = {
     "cc_mcmc_loglike_evals": (C.c_int64, [_vp]),
     "cc_mcmc_destroy": (None, [_vp]),
     "cc_nmath_batch": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_int64, c_dp]),
+    "cc_simulate_infxn_2_death": (C.c_int, [C.c_int, c_dp, C.c_int32, c_dp, c_dp, c_dp, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, C.c_uint64, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
     "cc_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
     "cc_dmma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "cc_last_kernel_ms": (C.c_int, [_vp, c_dp, C.POINTER(C.c_int32)]),
@@ -297,7 +299,7 @@ class Mcmc:
         return dict(beta=beta, mc_accept=mc, move_accept=mv, bw=bw.reshape(self.chains, self.rungs, self.d))
 
 
-FN = dict(pgamma=1, dpois=2, dbinom=3, dnorm=4, dbeta=5, dunif=6, pweibull=7, stirlerr=8, bd0=9, fastlog=10)
+FN = dict(pgamma=1, dpois=2, dbinom=3, dnorm=4, dbeta=5, dunif=6, pweibull=7, stirlerr=8, bd0=9, fastlog=10, rpois=11)
 
 
 def nmath(fn: str, a, b=0.0, c=0.0, device: int = 0):
@@ -321,3 +323,18 @@ def dmma_probe(device: int = 0, iters: int = 4096, fma_per_mma: int = 0):
     a, b, ms = C.c_double(), C.c_double(), C.c_double()
     check(load().cc_dmma_probe(device, iters, fma_per_mma, C.byref(a), C.byref(b), C.byref(ms)))
     return a.value, b.value, ms.value
+
+
+def simulate_infxn_2_death(infections, ifr, rho, popN, m_od, s_od, sero_delay_rate, smplfrac=1.0, seed=1, n_rep=1, device=0):
+    """cc_simulate_infxn_2_death: daily death and seroconversion counts [n_rep][T][A] and their means [T][A]."""
+    inf = np.ascontiguousarray(infections, dtype=np.float64)
+    ifr, rho, popN = (np.ascontiguousarray(v, dtype=np.float64) for v in (ifr, rho, popN))
+    T, A = inf.size, ifr.size
+    if rho.size != A or popN.size != A:
+        raise ValueError("ifr, rho and popN must have one entry per stratum")
+    deaths, sero = np.empty((n_rep, T, A)), np.empty((n_rep, T, A))
+    md, ms = np.empty((T, A)), np.empty((T, A))
+    check(load().cc_simulate_infxn_2_death(device, _dp(inf), T, _dp(ifr), _dp(rho), _dp(popN), A, float(m_od), float(s_od),
+                                           float(sero_delay_rate), float(smplfrac), int(seed), int(n_rep), _dp(deaths), _dp(sero),
+                                           _dp(md), _dp(ms)))
+    return dict(deaths=deaths, serocon=sero, mean_deaths=md, mean_serocon=ms)

@@ -1,0 +1,107 @@
+// cc_sim.cuh - device-side forward simulator, the aggregate form of
+// /root/reference/R/simulators.R:114-263 (Agesim_infxn_2_death) and :1-92 (sim_seroprev).
+//
+// The reference draws I_t ~ Poisson(infections[t]) infections per day, splits them over the strata with a multinomial
+// (probability P_a = popN_a Rho_a / sum), materialises ONE ROW PER INFECTION, and then draws per row: death (Bernoulli IFR_a),
+// onset-to-death time (gamma, shape 1/s_od^2, scale m_od s_od^2), time to seroconversion (exponential, mean
+// sero_delay_rate), inclusion in the serosurvey (Bernoulli smplfrac); events are binned to the day they fall in,
+// (j-1, j], and events after curr_day are dropped.  By Poisson splitting / thinning every (day, stratum) cell of the
+// aggregated tables is an INDEPENDENT Poisson count whose mean is the discrete convolution of the infection curve with the
+// delay's interval masses - the line list is never needed:
+//     Deaths[j][a]       ~ Poisson( P_a IFR_a      sum_{t<=j} infections[t] (G(j-t+1) - G(j-t)) )       G = gamma cdf
+//     SeroConverts[j][a] ~ Poisson( P_a smplfrac   sum_{t<=j} infections[t] (H(j-t+1) - H(j-t)) )       H = exponential cdf
+// (the same convolutions as the likelihood, binomial.cpp:187-193,288-298).  Seroreversion couples the conversion and the
+// reversion day of one person and is not simulated here (the host mirror says so).
+// Random numbers: Philox4x32-10 keyed by (seed, "SIMU", replicate, cell, draw counter) - reproducible for a seed and
+// independent of the launch shape; NOT R's Mersenne-Twister stream (parity is distributional).
+#pragma once
+#include "cc_rng.cuh"
+#include "nmath_dev.cuh"
+
+namespace ccdev {
+
+constexpr uint32_t kStreamSim = 0x53494d55u;  // "SIMU"
+
+struct SimRng {
+  uint64_t seed;
+  uint32_t rep, cell, kind, ctr;
+  ccrng::u4 buf;
+  int have;
+  __device__ double next() {  // uniform (0, 1), two per Philox block
+    if (have == 0) {
+      ccrng::u4 c;
+      c.x = ctr++; c.y = kind; c.z = cell; c.w = rep;
+      buf = ccrng::philox4x32_10(c, (uint32_t)seed ^ kStreamSim, (uint32_t)(seed >> 32));
+      have = 2;
+    }
+    have--;
+    return have == 1 ? ccrng::u01(buf.x, buf.y) : ccrng::u01(buf.z, buf.w);
+  }
+};
+
+// Poisson(lam): sequential-search inversion below 10, Hoermann's transformed rejection (PTRS, 1993) from 10 up
+__device__ inline double rpois_dev(double lam, SimRng& g) {
+  if (!(lam > 0.0)) return (lam == 0.0) ? 0.0 : d_nan();
+  if (!isfinite(lam)) return d_nan();
+  if (lam < 10.0) {
+    const double u = g.next();
+    double p = exp(-lam), s = p;
+    int k = 0;
+    while (u > s && k < 200) {
+      k++;
+      p *= lam / (double)k;
+      s += p;
+    }
+    return (double)k;
+  }
+  const double slam = sqrt(lam), loglam = log(lam);
+  const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+  const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+  for (int it = 0; it < 1000; it++) {
+    const double U = g.next() - 0.5, V = g.next();
+    const double us = 0.5 - fabs(U);
+    const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+    if (us >= 0.07 && V <= vr) return k;
+    if (k < 0.0 || (us < 0.013 && V > us)) continue;
+    if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
+  }
+  return floor(lam);  // unreachable in practice (acceptance > 0.9 per round)
+}
+
+// means of the per-day counts: mu_d[j] = sum_t inf[t] dG(j - t), mu_s[j] = sum_t inf[t] dH(j - t); one block
+__global__ void sim_means_kernel(const double* __restrict__ inf, int T, double m_od, double s_od, double sero_rate,
+                                 double* __restrict__ dG, double* __restrict__ dH, double* __restrict__ mu_d, double* __restrict__ mu_s) {
+  const double alph = 1.0 / (s_od * s_od), scale = m_od * (s_od * s_od);
+  const GammaShape gs = gamma_shape(alph);
+  for (int k = threadIdx.x; k < T; k += blockDim.x) {
+    dG[k] = pgamma_lower(gs, (double)(k + 1) / scale) - pgamma_lower(gs, (double)k / scale);
+    dH[k] = exp(-(double)k / sero_rate) * (-expm1(-1.0 / sero_rate));  // H(k+1) - H(k)
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t <= j; t++) {
+      a = fma(inf[t], dG[j - t], a);
+      b = fma(inf[t], dH[j - t], b);
+    }
+    mu_d[j] = a;
+    mu_s[j] = b;
+  }
+}
+
+// one thread per (replicate, day, stratum): the two Poisson counts of the cell
+__global__ void sim_draw_kernel(const double* __restrict__ mu_d, const double* __restrict__ mu_s, const double* __restrict__ w_death,
+                                const double* __restrict__ w_sero, int T, int A, long long n_rep, unsigned long long seed,
+                                double* __restrict__ deaths, double* __restrict__ serocon) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cells = (long long)T * A;
+  if (idx >= n_rep * cells) return;
+  const long long rep = idx / cells;
+  const int cell = (int)(idx - rep * cells), j = cell / A, a = cell - j * A;
+  SimRng g{seed, (uint32_t)rep, (uint32_t)cell, 0u, 0u, {0, 0, 0, 0}, 0};
+  deaths[idx] = rpois_dev(mu_d[j] * w_death[a], g);
+  g.kind = 1u; g.ctr = 0u; g.have = 0;
+  serocon[idx] = rpois_dev(mu_s[j] * w_sero[a], g);
+}
+
+}  // namespace ccdev

@@ -21,6 +21,7 @@
 #include "cc_eval_tile.cuh"
 #include "cc_mcmc_dev.cuh"
 #include "cc_model.cuh"
+#include "cc_sim.cuh"
 
 using namespace ccdev;
 
@@ -1441,6 +1442,11 @@ __global__ void nmath_kernel(int fn, const double* __restrict__ a, const double*
     case CC_FN_STIRLERR: r = stirlerr(x); break;
     case CC_FN_BD0: r = bd0(x, y); break;
     case CC_FN_FASTLOG: r = fast_log(x, tab); break;
+    case CC_FN_RPOIS: {
+      SimRng g{(unsigned long long)z, (uint32_t)y, (uint32_t)(i & 0xffffffffLL), 7u, 0u, {0, 0, 0, 0}, 0};
+      r = rpois_dev(x, g);
+      break;
+    }
     default: r = d_nan();
   }
   out[i] = r;
@@ -1448,7 +1454,7 @@ __global__ void nmath_kernel(int fn, const double* __restrict__ a, const double*
 
 extern "C" int cc_nmath_batch(int device, int fn, const double* a, const double* b, const double* c, int64_t n, double* out) {
   if (!a || !b || !c || !out || n < 0) return fail(CC_E_INVALID, "cc_nmath_batch: bad argument");
-  if (fn < CC_FN_PGAMMA || fn > CC_FN_FASTLOG) return fail(CC_E_INVALID, "cc_nmath_batch: unknown function id");
+  if (fn < CC_FN_PGAMMA || fn > CC_FN_RPOIS) return fail(CC_E_INVALID, "cc_nmath_batch: unknown function id");
   if (cc_device_count() <= 0) return fail(CC_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
   if (n == 0) return CC_OK;
   CC_CUDA(cudaSetDevice(device));
@@ -1551,5 +1557,68 @@ extern "C" int cc_dmma_probe(int device, int iters, int fma_per_mma, double* mma
   if (mma_tflops) *mma_tflops = mma_flops / ((double)best * 1e-3) / 1e12;
   if (fma_tflops) *fma_tflops = fma_flops / ((double)best * 1e-3) / 1e12;
   if (ms_out) *ms_out = best;
+  return CC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward simulator
+extern "C" int cc_simulate_infxn_2_death(int device, const double* infections, int32_t T, const double* ifr, const double* rho,
+                                         const double* popN, int32_t A, double m_od, double s_od, double sero_delay_rate,
+                                         double smplfrac, uint64_t seed, int64_t n_rep, double* deaths, double* serocon,
+                                         double* mean_deaths, double* mean_serocon) {
+  if (!infections || !ifr || !rho || !popN) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: null argument");
+  if (T < 1 || A < 1 || n_rep < 0) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: need T >= 1, A >= 1, n_rep >= 0");
+  if (n_rep > 0 && (!deaths || !serocon)) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: null output");
+  if (!(m_od > 0.0) || !(s_od > 0.0) || !(sero_delay_rate > 0.0) || !(smplfrac > 0.0) || !(smplfrac <= 1.0))
+    return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: m_od, s_od, sero_delay_rate must be positive and smplfrac in (0, 1]");
+  if ((long long)n_rep * T * A > (1LL << 40)) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: too many cells");
+  if (cc_device_count() <= 0) return fail(CC_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  double wsum = 0.0;
+  for (int a = 0; a < A; a++) {
+    if (!(popN[a] >= 0.0) || !(rho[a] >= 0.0) || !(ifr[a] >= 0.0) || !(ifr[a] <= 1.0))
+      return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: popN, rho must be >= 0 and ifr in [0, 1]");
+    wsum += popN[a] * rho[a];
+  }
+  if (!(wsum > 0.0)) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: popN * rho sums to zero");
+  for (int t = 0; t < T; t++)
+    if (!(infections[t] >= 0.0) || !std::isfinite(infections[t]))
+      return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: infections must be finite and >= 0");
+  std::vector<double> wd(A), ws(A);
+  for (int a = 0; a < A; a++) {
+    const double pa = popN[a] * rho[a] / wsum;  // simulators.R:172
+    wd[a] = pa * ifr[a];
+    ws[a] = pa * smplfrac;
+  }
+  CC_CUDA(cudaSetDevice(device));
+  const size_t cells = (size_t)T * A, tot = (size_t)n_rep * cells;
+  double* d = nullptr;
+  CC_CUDA(cudaMalloc((void**)&d, ((size_t)5 * T + 2 * A + 2 * std::max<size_t>(tot, 1)) * sizeof(double)));
+  double *d_inf = d, *d_dG = d + T, *d_dH = d + 2 * T, *d_mud = d + 3 * T, *d_mus = d + 4 * T, *d_wd = d + 5 * T, *d_ws = d_wd + A,
+         *d_deaths = d_ws + A, *d_sero = d_deaths + std::max<size_t>(tot, 1);
+  cudaError_t e = cudaMemcpy(d_inf, infections, (size_t)T * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_wd, wd.data(), (size_t)A * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_ws, ws.data(), (size_t)A * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    sim_means_kernel<<<1, 256>>>(d_inf, T, m_od, s_od, sero_delay_rate, d_dG, d_dH, d_mud, d_mus);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && tot > 0) {
+    sim_draw_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(d_mud, d_mus, d_wd, d_ws, T, A, (long long)n_rep, seed, d_deaths, d_sero);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && tot > 0) e = cudaMemcpy(deaths, d_deaths, tot * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tot > 0) e = cudaMemcpy(serocon, d_sero, tot * sizeof(double), cudaMemcpyDeviceToHost);
+  std::vector<double> mud, mus;
+  if (e == cudaSuccess && (mean_deaths || mean_serocon)) {
+    mud.resize(T); mus.resize(T);
+    e = cudaMemcpy(mud.data(), d_mud, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(mus.data(), d_mus, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(CC_E_CUDA, std::string("cc_simulate_infxn_2_death: ") + cudaGetErrorString(e));
+  for (int j = 0; j < T && (mean_deaths || mean_serocon); j++)
+    for (int a = 0; a < A; a++) {
+      if (mean_deaths) mean_deaths[(size_t)j * A + a] = mud[j] * wd[a];
+      if (mean_serocon) mean_serocon[(size_t)j * A + a] = mus[j] * ws[a];
+    }
   return CC_OK;
 }

@@ -216,6 +216,22 @@ void cc_mcmc_destroy(cc_mcmc* s);
 int cc_nmath_batch(int device, int fn, const double* a, const double* b, const double* c, int64_t n, double* out);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Forward simulator: the aggregate form of Agesim_infxn_2_death / sim_seroprev (R/simulators.R:114-263, :1-92).
+ * The reference materialises one row per infection; by Poisson thinning every (day, stratum) cell of its aggregated
+ * outputs is an independent Poisson count, drawn here directly on the device:
+ *   deaths[r][j][a]  ~ Poisson(P_a ifr_a    sum_{t<=j} infections[t] (G(j-t+1) - G(j-t))),  G = gamma(1/s_od^2, m_od s_od^2) cdf
+ *   serocon[r][j][a] ~ Poisson(P_a smplfrac sum_{t<=j} infections[t] (H(j-t+1) - H(j-t))),  H = exponential cdf, mean sero_delay_rate
+ * with P_a = popN_a rho_a / sum(popN rho).  `deaths`, `serocon`: host arrays [n_rep][T][A] (daily counts; the caller
+ * accumulates).  `mean_deaths`, `mean_serocon`: optional host arrays [T][A] of the cell means.  Seroreversion is not
+ * simulated.  Random numbers: Philox keyed by (seed, replicate, cell); parity with R's stream is distributional only.
+ * --------------------------------------------------------------------------------------------------------- */
+int cc_simulate_infxn_2_death(int device, const double* infections, int32_t T, const double* ifr, const double* rho,
+                              const double* popN, int32_t A, double m_od, double s_od, double sero_delay_rate, double smplfrac,
+                              uint64_t seed, int64_t n_rep, double* deaths, double* serocon, double* mean_deaths,
+                              double* mean_serocon);
+#define CC_FN_RPOIS 11 /* test hook: one Poisson draw, a = mean, b = replicate id, c = seed */
+
+/* ---------------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): live FP64 FMA peak of the device, and kernel time of the last batch call.
  * --------------------------------------------------------------------------------------------------------- */
 /* Register-resident DFMA chain micro-benchmark; returns achieved TFLOP/s (FMA = 2 flops) in *tflops. */
