@@ -6,7 +6,7 @@ B="python bench.py --steps 8 --warmup 3 --no-cpu-baseline --mcmc-iters 0"
 for lib in build_variants/*.so; do
   n=$(basename $lib .so)
   for rep in 1 2; do
-    CCB200_LIB=$PWD/$lib $B > $O/var_$n.json 2> $O/var_$n.err; rc=$?
+    CC_VERBOSE=1 CCB200_LIB=$PWD/$lib $B > $O/var_$n.json 2> $O/var_$n.err; rc=$?; grep "per-day pass" $O/var_$n.err | head -1
     python - $O/var_$n.json $rc <<'PY'
 import json,sys
 try:
