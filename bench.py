@@ -249,6 +249,15 @@ def main():
     wall = max_over_ranks(time.perf_counter() - wall0)
     e2e_value = V * world * e2e_steps / wall
     assert np.array_equal(h_out.numpy(), ll), "host path and device path must agree bit for bit"
+    # the PCIe ceiling of that leg: the same pinned buffer copied alone (reported, not part of any timed region above)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_theta.copy_(h_theta, non_blocking=True)
+    c0.record()
+    for _ in range(3):
+        d_theta.copy_(h_theta, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * d * V * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
 
     # ---------------------------------------------------------------- MCMC leg (configs[2]: 64 chains x 50 rungs per GPU)
     mcmc = None
@@ -322,7 +331,8 @@ def main():
             "config": {"workload": "cfg5: likelihood-only, 10 age bands x 300 days x 5 knots x 3 serosurveys, binomial (d=34)",
                        "vectors_per_gpu_per_step": V, "layout": "SoA theta[d][V]", "l2": "inputs larger than L2 (%.0f MB per step)" % (d * V * 8 / 1e6),
                        "full_eval_fraction": full_frac},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": d * V * 8, "d2h_bytes_per_step": V * 8, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": d * V * 8, "d2h_bytes_per_step": V * 8, "steps": e2e_steps,
+                    "h2d_gbs_measured": h2d_gbs, "h2d_bound": h2d_gbs * 1e9 / (d * 8) * world},
             "gpu_launches": args.steps * 5,  # phase-1 pass, bucket offsets, scatter, phase-2 pass, phase-3 pass per step
             "posterior_like": {"value": value_post, "unit": UNIT, "frac_of_fp64_peak": value_post * falg / 1e12 / peak_tf,
                                "vectors": "truth x (1 + 0.02 N(0,1)), clipped to the box"},

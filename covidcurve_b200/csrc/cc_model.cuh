@@ -73,6 +73,7 @@ struct cc_model {
   double* d_out = nullptr; size_t d_out_bytes = 0;
   std::vector<double> pinit;
   int sm_count = 0;
+  int grid_p2 = 1;                 // resident CTAs of pass C of the batched likelihood
   int grid_max = 1;                // resident CTAs of the evaluation kernel on this device
   // work buffers of the batched likelihood, one set per launch slot ([0] device-pointer calls, [1],[2] the two host-path
   // streams): records rec[F][cap], regime keys, permutation, histogram + cursors; grown on demand

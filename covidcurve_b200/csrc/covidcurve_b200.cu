@@ -52,16 +52,33 @@ extern "C" int cc_device_count(void) {
 // ------------------------------------------------------------------------------------------------ kernels
 constexpr int kEvalThreads = 128;
 
+#ifndef CC_P2_SYNC
+#define CC_P2_SYNC 1   // 1: the warps of a CTA start every evaluation together; 2: every stage (developer experiments); 0: free-running
+#endif
 constexpr int kWarpsPerCta = 4;
+// Shape of pass C of the batched likelihood: few LARGE CTAs whose warps start every evaluation together.  The per-day code
+// is ~100 kB of instructions per evaluation, far beyond the SM's instruction cache: free-running warps each stream it from
+// L2 (ncu: `no_instruction` was the top stall of the box workload, 3.4 per issue); warps of one CTA that run the same stage at
+// the same time share one stream.  Full lock-step (a barrier per stage) loses again because the FP64-heavy stages then
+// collide on the pipe.  Measured on B200, box workload, M evals/s (value / e2e): 5 CTAs x 4 warps free-running 73.8 / 63.5;
+// the same with the barrier 77.9 / 68; 2 x 8: 79.5 / 74.3; 2 x 10: 83.1 / 74.7; 1 x 20: 80.6 / 77.1; 2 x 10 with a barrier
+// per stage 78.9 / 74.9 (profiles/r1_summary.md).
+#ifdef CC_P2_WARPS
+__host__ __device__ constexpr int p2_warps(int) { return CC_P2_WARPS; }
+#else
+__host__ __device__ constexpr int p2_warps(int nt) { return nt <= 5 ? 10 : nt <= 7 ? 7 : 6; }  // 11.2 / 15.3 / 33 kB of shared memory per warp
+#endif
+#ifdef CC_P2_CTAS
+__host__ __device__ constexpr int p2_ctas(int) { return CC_P2_CTAS; }
+#else
+__host__ __device__ constexpr int p2_ctas(int nt) { return nt <= 7 ? 2 : 1; }
+#endif
 #ifndef CC_MIN_CTAS
 #define CC_MIN_CTAS 4  // resident CTAs per SM the evaluation kernels are compiled for (caps registers at 128 per thread)
 #endif
 #ifndef CC_SWEEP_CTAS
 #define CC_SWEEP_CTAS 3  // resident 4-warp CTAs per SM the cached Metropolis sweep is compiled for (caps registers at 168)
 #endif
-#ifndef CC_P2_CTAS
-#define CC_P2_CTAS 5  // pass C of the batched likelihood up to 320 days: 5 CTAs x 4 warps fit the shared memory of an SM; 96 registers
-#endif                // (measured: 72.0 -> 73.8 M evals/s on the box workload against 4 CTAs / 128 registers)
 
 // ---- batched likelihood as a two-pass pipeline --------------------------------------------------------------------
 // pass A (one THREAD per vector): phase 1 -> record rec[f * cap + v] in global memory, a regime key, a histogram of the keys
@@ -127,32 +144,82 @@ __global__ void bucket_scatter_kernel(const int* __restrict__ key, long long n, 
   }
 }
 
+// tile_phase2 with a CTA barrier in front of every stage: all warps of the CTA execute the same stage code at the same
+// time, so the SM fetches one instruction stream per CTA instead of one per warp.  `live` = this warp has a vector.
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, (NT <= 5) ? CC_P2_CTAS : CC_MIN_CTAS) loglike_phase2_kernel(const KModel m, long long n, double* __restrict__ rec,
+__device__ __forceinline__ void cta_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr,
+                                           long long stride, bool live) {
+  const int lane = threadIdx.x & 31;
+  __syncthreads();
+  if (live) {
+    for (int f = lane; f < L.n2; f += 32) w.rec[f] = scr[f * stride];
+    __syncwarp();
+    live = w.rec[L.flags] != 0.0;  // knots not increasing: pass D returns the failure value
+  }
+  if (live) tile_sero_prefix<NT>(m, L, w, tb);
+  __syncthreads();
+  if (live) tile_gamma<NT>(m, L, w, tb);
+  __syncthreads();
+  if (live) {
+    const double tot = stage_spline<NT>(m, L, w.rec, w.xs);
+    const bool ok = stage_popn(m, L, w.rec, tot);
+    if (lane == 0) scr[L.o_status * stride] = ok ? 0.0 : 1.0;
+    live = ok;
+    __syncwarp();
+  }
+  __syncthreads();
+  if (live) stage_conv<NT>(m, w.xs, w.gs, w.auc, conv_lag_blocks(m, L, w.rec));
+  __syncthreads();
+  if (live) {
+    double l1, s_all, s_unc;
+    stage_l1_direct(m, tb, w.auc, w.rec[L.snm], l1, s_all, s_unc);
+    if (lane == 0) {
+      scr[L.o_l1 * stride] = l1 - m.l1_const;
+      scr[L.o_texpd * stride] = s_all;
+      scr[L.o_sunc * stride] = s_unc;
+    }
+    stage_surveys(m, w.xs, w.sk, [&](int sv, double v) { scr[(L.o_base + sv) * stride] = v; });
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2_kernel(const KModel m, long long n, double* __restrict__ rec,
                                                                                           long long cap, const int* __restrict__ perm,
                                                                                           unsigned int* __restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned int s_ticket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
   const TileTables tb = tile_tables_load(m, nullptr);
   const TileSmem w = carve_tile(reinterpret_cast<double*>(smem_raw) + (size_t)warp * tile_smem_doubles(m.K, m.A, m.S, NT), L, NT);
   tile_smem_init(w);
-  // dynamic queue of kPhase2Tile-vector tiles in bucket order (heavy regimes first): a warp that drew cheap vectors comes
-  // back for more, so the launch ends within one short tile of the ideal instead of one 32-vector tile of the worst regime
+  // dynamic queue of CTA tiles (kPhase2Tile vectors per warp) in bucket order (heavy regimes first): a CTA that drew cheap
+  // vectors comes back for more, so the launch ends within one short tile of the ideal instead of one long tile of the
+  // worst regime
   for (;;) {
-    unsigned int tk = 0;
-    if (lane == 0) tk = atomicAdd(ticket, 1u);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    const long long t0 = (long long)tk * kPhase2Tile;
-    if (t0 >= n) break;
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const long long c0 = (long long)s_ticket * (kPhase2Tile * p2_warps(NT));
+    if (c0 >= n) break;
+    const long long t0 = c0 + (long long)warp * kPhase2Tile;
     const long long pos = t0 + lane;
     const int vl = (lane < kPhase2Tile && pos < n) ? perm[pos] : 0;
-    const int cnt = (int)min((long long)kPhase2Tile, n - t0);
-    for (int e = 0; e < cnt; e++) {
-      const long long v = __shfl_sync(0xffffffffu, vl, e);
-      tile_phase2<NT>(m, L, w, tb, rec + v, (int)0, cap);
+    const int cnt = (int)max((long long)0, min((long long)kPhase2Tile, n - t0));
+    for (int e = 0; e < kPhase2Tile; e++) {
+#if CC_P2_SYNC == 2
+      const long long v = __shfl_sync(0xffffffffu, vl, min(e, max(cnt - 1, 0)));
+      cta_phase2<NT>(m, L, w, tb, rec + v, cap, e < cnt);
+#else
+#if CC_P2_SYNC == 1
+      __syncthreads();  // the warps of the CTA start every evaluation together
+#endif
+      if (e < cnt) {
+        const long long v = __shfl_sync(0xffffffffu, vl, e);
+        tile_phase2<NT>(m, L, w, tb, rec + v, (int)0, cap);
+      }
+#endif
     }
-    __syncwarp();
   }
 }
 
@@ -652,7 +719,7 @@ static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
   cudaError_t e = cudaSuccess;
 #define CC_OPT(NT_)                                                                                                   \
   if (nt == NT_) {                                                                                                    \
-    e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);           \
+    e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes / kWarpsPerCta * p2_warps(NT_)); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_cached_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
   }
@@ -875,8 +942,10 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   if (e == cudaSuccess) {
     int bps = 0;
     const size_t sm_bytes = warp_cta_smem(k, m->nt);
+    const int p2w = p2_warps(m->nt);
+    const size_t p2_bytes = sm_bytes / kWarpsPerCta * p2w;
     switch (m->nt) {
-#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_phase2_kernel<NT_>, 32 * kWarpsPerCta, sm_bytes); break;
+#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_phase2_kernel<NT_>, 32 * p2_warps(NT_), p2_bytes); break;
       CC_FOR_EACH_NT(CC_OCC)
 #undef CC_OCC
       default: break;
@@ -885,10 +954,11 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
       cc_model_destroy(m);
       return fail(CC_E_INVALID, "model too large for one CTA's shared memory");
     }
-    m->grid_max = std::max(1, bps) * m->sm_count;
+    m->grid_p2 = std::max(1, bps) * m->sm_count;
+    m->grid_max = std::max(1, bps * p2w / kWarpsPerCta) * m->sm_count;  // in 4-warp CTAs (initial-state kernel of the sweep)
     if (std::getenv("CC_VERBOSE"))
-      std::fprintf(stderr, "covidcurve_b200: per-day pass %d CTAs/SM x %d warps, %zu B smem/CTA, persistent grid %d\n", bps, kWarpsPerCta,
-                   sm_bytes, m->grid_max);
+      std::fprintf(stderr, "covidcurve_b200: per-day pass %d CTAs/SM x %d warps, %zu B smem/CTA, persistent grid %d\n", bps, p2w,
+                   p2_bytes, m->grid_p2);
   }
   const size_t smem = eval_smem_bytes(d, T, T);
   if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(curves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -968,14 +1038,15 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
   const unsigned gridA = (unsigned)((n + 127) / 128);
   const size_t smem = warp_cta_smem(k, m->nt);
   const long long tiles = (n + kPhase2Tile - 1) / kPhase2Tile;
-  const unsigned gridC = (unsigned)std::min<long long>((tiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)m->grid_max);
+  const int p2w = p2_warps(m->nt);
+  const unsigned gridC = (unsigned)std::min<long long>((tiles + p2w - 1) / p2w, (long long)m->grid_p2);
   switch (m->nt) {
 #define CC_LAUNCH(NT_)                                                                                                        \
   case NT_:                                                                                                                   \
     loglike_phase1_kernel<NT_><<<gridA, 128, 0, st>>>(k, d_theta, n, ld, wk.rec, wk.cap, wk.key, counts);                     \
     bucket_offsets_kernel<<<1, 1, 0, st>>>(counts, cursor);                                                                   \
     bucket_scatter_kernel<<<gridA, 128, 0, st>>>(wk.key, n, cursor, wk.perm);                                                 \
-    loglike_phase2_kernel<NT_><<<gridC, 32 * kWarpsPerCta, smem, st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 6);                      \
+    loglike_phase2_kernel<NT_><<<gridC, 32 * p2_warps(NT_), smem / kWarpsPerCta * p2_warps(NT_), st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 6);                      \
     loglike_phase3_kernel<<<gridA, 128, 0, st>>>(k, n, wk.rec, wk.cap, d_out);                                                \
     break;
     CC_FOR_EACH_NT(CC_LAUNCH)
