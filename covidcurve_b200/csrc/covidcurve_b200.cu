@@ -76,9 +76,20 @@ __host__ __device__ constexpr int p2_ctas(int nt) { return nt <= 7 ? 2 : 1; }
 #ifndef CC_MIN_CTAS
 #define CC_MIN_CTAS 4  // resident CTAs per SM the evaluation kernels are compiled for (caps registers at 128 per thread)
 #endif
+// The cached Metropolis sweep runs as ONE 12-warp CTA per SM (168 registers, 15.5 kB of shared memory per warp at cfg3)
+// whose warps start every single-site update together: same parameter, same stages, one instruction stream
+// (measured, cfg3 64 x 50: 3 CTAs x 4 free-running warps 1.52 M iterations/s, 1 x 12 free-running 1.51, 1 x 12 with the
+// barrier 1.63, 1 x 14 with the barrier 1.62).
 #ifndef CC_SWEEP_CTAS
-#define CC_SWEEP_CTAS 3  // resident 4-warp CTAs per SM the cached Metropolis sweep is compiled for (caps registers at 168)
+#define CC_SWEEP_CTAS 1
 #endif
+#ifndef CC_SWEEP_WARPS
+#define CC_SWEEP_WARPS 12
+#endif
+#ifndef CC_SWEEP_SYNC
+#define CC_SWEEP_SYNC 1
+#endif
+constexpr int kSweepWarps = CC_SWEEP_WARPS;
 
 // ---- batched likelihood as a two-pass pipeline --------------------------------------------------------------------
 // pass A (one THREAD per vector): phase 1 -> record rec[f * cap + v] in global memory, a regime key, a histogram of the keys
@@ -346,7 +357,7 @@ __device__ __forceinline__ void warp_copy(double* dst, double* src, int n) {
 // both.  Every cached quantity is a pure function of the current parameter vector, so the values equal a from-scratch
 // evaluation.  `iteration` is the 1-based drjacoby iteration this sweep produces (2 .. burnin+samples).
 template <int NT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_cached_kernel(const KModel m, const McmcState s, int iteration) {
+__global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_cached_kernel(const KModel m, const McmcState s, int iteration) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
@@ -391,7 +402,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
     __syncwarp();
   };
 
-  for (int b = gwarp; b < P; b += nwarps) {
+  // named barrier shared by the warps of the CTA; arrivals are counted per warp, wherever in the code the warp is
+  auto cta_bar = [&]() {
+#if CC_SWEEP_SYNC
+    asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");
+#endif
+  };
+  for (int b0 = 0; b0 < P; b0 += nwarps) {
+    const int b = b0 + gwarp;
+    if (b >= P) {  // no particle left for this warp in the last round: keep the CTA's barrier count
+      for (int i = 0; i < d; i++) cta_bar();
+      continue;
+    }
     const int c = b / s.rungs, r = b - c * s.rungs;
     const int pid = s.at_rung[b];  // particle (within chain) sitting at rung position r
     const int p = c * s.rungs + pid;
@@ -445,6 +467,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_SWEEP_CTAS) mcmc_sweep_c
     __syncwarp();
 
     for (int i = 0; i < d; i++) {
+      cta_bar();  // the warps of the CTA work on the same parameter (same stages, same code) at the same time
       const int dep = m.dep[i];
       const double thp = w.q_thp[i], php = w.q_php[i], adj = w.q_adj[i];
       auto par = [&](int j) { return j == i ? thp : w.pcur[j]; };
@@ -1354,7 +1377,7 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
       // warps per CTA and CTAs per SM of the sweep: whatever keeps the most warps resident (shared memory and registers)
       const size_t per_warp = sweep_smem_doubles(d, m->k.K, m->k.A, m->k.S, m->nt) * sizeof(double);
       int best_wpc = 0, best_warps = 0, best_ctas = 0;
-      for (int wpc = kWarpsPerCta; wpc >= 1; wpc >>= 1) {
+      for (int wpc = kSweepWarps; wpc >= 1; wpc = (wpc > 4) ? wpc - 2 : wpc >> 1) {
         int ctas = 0;
         cudaError_t oe = cudaSuccess;
         switch (m->nt) {
