@@ -129,3 +129,26 @@ def test_posterior_downsample_is_weighted_without_replacement():
     with pytest.raises(ValueError):
         posterior._downsample(fit, None, n + 1, seed=3)
     np.testing.assert_allclose(posterior.convert_post_probs(ll).sum(), 1.0, rtol=1e-12)
+
+
+def test_simulator_mirror_validates_like_the_reference():
+    """R/simulators.R:124-147: the argument checks run before any device work."""
+    from covidcurve_b200 import simulators
+    fat = pd.DataFrame({"Strata": ["ma1", "ma2"], "IFR": [0.01, 0.1], "Rho": [1.0, 1.0]})
+    demog = pd.DataFrame({"Strata": ["ma1", "ma2"], "popN": [1e5, 2e5]})
+    inf = np.full(50, 10.0)
+    kw = dict(curr_day=50, spec=0.95, sens=0.85, demog=demog, sero_delay_rate=18.3)
+    with pytest.raises(ValueError, match="Strata, IFR, Rho"):
+        simulators.Agesim_infxn_2_death(fat.rename(columns={"Rho": "rho"}), inf, **kw)
+    with pytest.raises(ValueError, match="same order"):
+        simulators.Agesim_infxn_2_death(fat, inf, **dict(kw, demog=demog.iloc[::-1].reset_index(drop=True)))
+    with pytest.raises(ValueError, match="one entry per day"):
+        simulators.Agesim_infxn_2_death(fat, inf[:-1], **kw)
+    with pytest.raises(ValueError, match="spec"):
+        simulators.Agesim_infxn_2_death(fat, inf, **dict(kw, spec=1.5))
+    with pytest.raises(ValueError, match="smplfrac"):
+        simulators.Agesim_infxn_2_death(fat, inf, smplfrac=0.0, **kw)
+    with pytest.raises(NotImplementedError):
+        simulators.Agesim_infxn_2_death(fat, inf, simulate_seroreversion=True, sero_rev_shape=3.0, sero_rev_scale=140.0, **kw)
+    with pytest.raises(NotImplementedError):
+        simulators.Agesim_infxn_2_death(fat, inf, return_linelist=True, **kw)
