@@ -514,20 +514,27 @@ __device__ inline double stage_spline(const KModel& m, const RecLayout& L, const
   // interval thresholds in registers (the common K = 5 has three); longer knot vectors fall back to shared memory
   const double cd0 = (K > 2) ? rec[L.cday] : 1e300, cd1 = (K > 3) ? rec[L.cday + 1] : 1e300, cd2 = (K > 4) ? rec[L.cday + 2] : 1e300;
   const double y0 = rec[L.spl + 1];
-#pragma unroll 2
-  for (int i = lane; i < 64 * NT; i += 32) {
-    double v = 0.0;
-    if (i < T) {
-      const double di = (double)i;
+  // two days per lane and round, branch-free (days beyond T are evaluated at T - 1 and zeroed): the two exp() chains are
+  // adjacent in the instruction stream and the compiler interleaves them
+#pragma unroll 1
+  for (int i0 = lane; i0 < 64 * NT; i0 += 64) {
+    double v[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = i0 + 32 * u, ic = min(i, T - 1);
+      const double di = (double)ic;
       int j = ((cd0 < di) ? 1 : 0) + ((cd1 < di) ? 1 : 0) + ((cd2 < di) ? 1 : 0);
       for (int mI = 3; mI < K - 2; mI++) j += (rec[L.cday + mI] < di) ? 1 : 0;
       const double* c = rec + L.spl + 5 * j;
-      const double dx = (double)(i + 1) - c[0];
-      const double y = (i == 0) ? y0 : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
-      v = exp(y);
-      tot += v;
+      const double dx = (double)(ic + 1) - c[0];
+      const double y = (ic == 0) ? y0 : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
+      const double ev = exp(y);
+      v[u] = (i < T) ? ev : 0.0;
     }
-    xs[xs_index(i)] = v;
+    tot += v[0];
+    tot += v[1];
+    xs[xs_index(i0)] = v[0];
+    xs[xs_index(i0 + 32)] = v[1];
   }
   return warp_sum(tot);
 }
