@@ -78,7 +78,7 @@ SYMBOLS = {
     "cc_mcmc_destroy": (None, [_vp]),
     "cc_nmath_batch": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_int64, c_dp]),
     "cc_simulate_infxn_2_death": (C.c_int, [C.c_int, c_dp, C.c_int32, c_dp, c_dp, c_dp, C.c_int32, C.c_double, C.c_double, C.c_double,
-                                            C.c_double, C.c_uint64, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
+                                            C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "cc_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
     "cc_dmma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "cc_last_kernel_ms": (C.c_int, [_vp, c_dp, C.POINTER(C.c_int32)]),
@@ -325,16 +325,24 @@ def dmma_probe(device: int = 0, iters: int = 4096, fma_per_mma: int = 0):
     return a.value, b.value, ms.value
 
 
-def simulate_infxn_2_death(infections, ifr, rho, popN, m_od, s_od, sero_delay_rate, smplfrac=1.0, seed=1, n_rep=1, device=0):
-    """cc_simulate_infxn_2_death: daily death and seroconversion counts [n_rep][T][A] and their means [T][A]."""
+def simulate_infxn_2_death(infections, ifr, rho, popN, m_od, s_od, sero_delay_rate, smplfrac=1.0, seed=1, n_rep=1, device=0,
+                           sero_rev_shape=None, sero_rev_scale=None):
+    """cc_simulate_infxn_2_death: daily death, seroconversion (and, with the Weibull parameters, seroreversion) counts
+    [n_rep][T][A] and the means [T][A] of the first two."""
     inf = np.ascontiguousarray(infections, dtype=np.float64)
     ifr, rho, popN = (np.ascontiguousarray(v, dtype=np.float64) for v in (ifr, rho, popN))
     T, A = inf.size, ifr.size
     if rho.size != A or popN.size != A:
         raise ValueError("ifr, rho and popN must have one entry per stratum")
+    rev = sero_rev_shape is not None or sero_rev_scale is not None
     deaths, sero = np.empty((n_rep, T, A)), np.empty((n_rep, T, A))
+    srev = np.empty((n_rep, T, A)) if rev else None
     md, ms = np.empty((T, A)), np.empty((T, A))
     check(load().cc_simulate_infxn_2_death(device, _dp(inf), T, _dp(ifr), _dp(rho), _dp(popN), A, float(m_od), float(s_od),
-                                           float(sero_delay_rate), float(smplfrac), int(seed), int(n_rep), _dp(deaths), _dp(sero),
-                                           _dp(md), _dp(ms)))
-    return dict(deaths=deaths, serocon=sero, mean_deaths=md, mean_serocon=ms)
+                                           float(sero_delay_rate), float(smplfrac), float(sero_rev_shape or 0.0) if rev else 0.0,
+                                           float(sero_rev_scale or 0.0) if rev else 0.0, int(seed), int(n_rep), _dp(deaths), _dp(sero),
+                                           _dp(srev) if rev else None, _dp(md), _dp(ms)))
+    out = dict(deaths=deaths, serocon=sero, mean_deaths=md, mean_serocon=ms)
+    if rev:
+        out["serorev"] = srev
+    return out

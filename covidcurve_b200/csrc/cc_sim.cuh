@@ -10,8 +10,13 @@
 // delay's interval masses - the line list is never needed:
 //     Deaths[j][a]       ~ Poisson( P_a IFR_a      sum_{t<=j} infections[t] (G(j-t+1) - G(j-t)) )       G = gamma cdf
 //     SeroConverts[j][a] ~ Poisson( P_a smplfrac   sum_{t<=j} infections[t] (H(j-t+1) - H(j-t)) )       H = exponential cdf
-// (the same convolutions as the likelihood, binomial.cpp:187-193,288-298).  Seroreversion couples the conversion and the
-// reversion day of one person and is not simulated here (the host mirror says so).
+// (the same convolutions as the likelihood, binomial.cpp:187-193,288-298).
+// Seroreversion (sim_seroprev, simulators.R:26-33: time from seroconversion to reversion ~ Weibull) couples the conversion
+// day c and the reversion day r of one person, so the independent cells are the PAIRS (c, r):
+//     N[c][r][a] ~ Poisson( P_a smplfrac sum_{t<=c} infections[t] pi(c - t, r - t) ),   r = c .. curr_day,
+//     pi(u, v) = int_u^{u+1} f_exp(s) [F_weib(v + 1 - s) - F_weib(max(v - s, 0))] ds       (16-point Gauss-Legendre),
+// plus the people who converted on day c and do not revert within the study.  Daily conversions are the row sums, daily
+// reversions the column sums.
 // Random numbers: Philox4x32-10 keyed by (seed, "SIMU", replicate, cell, draw counter) - reproducible for a seed and
 // independent of the launch shape; NOT R's Mersenne-Twister stream (parity is distributional).
 #pragma once
@@ -102,6 +107,69 @@ __global__ void sim_draw_kernel(const double* __restrict__ mu_d, const double* _
   deaths[idx] = rpois_dev(mu_d[j] * w_death[a], g);
   g.kind = 1u; g.ctr = 0u; g.have = 0;
   serocon[idx] = rpois_dev(mu_s[j] * w_sero[a], g);
+}
+
+
+// ------------------------------------------------------------------------------------------------ seroreversion
+// pi[u * T + v], 0 <= u <= v < T: probability that a person infected at time 0 seroconverts in (u, u+1] and reverts in
+// (v, v+1].  One thread per pair.
+__global__ void sim_serorev_pi_kernel(int T, double sero_rate, double shape, double scale, double* __restrict__ pi) {
+  const double gx[8] = {0.0950125098376374402, 0.2816035507792589132, 0.4580167776572273863, 0.6178762444026437484,
+                        0.7554044083550030339, 0.8656312023878317439, 0.9445750230732325761, 0.9894009349916499326};
+  const double gw[8] = {0.1894506104550684963, 0.1826034150449235888, 0.1691565193950025382, 0.1495959888165767321,
+                        0.1246289712555338720, 0.0951585116824927848, 0.0622535239386478929, 0.0271524594117540949};
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * T) return;
+  const int u = (int)(idx / T), v = (int)(idx - (long long)u * T);
+  double acc = 0.0;
+  if (v >= u) {
+    for (int q = 0; q < 16; q++) {
+      const double xq = (q < 8) ? -gx[7 - q] : gx[q - 8], wq = (q < 8) ? gw[7 - q] : gw[q - 8];
+      const double sq = (double)u + 0.5 + 0.5 * xq;
+      const double f = exp(-sq / sero_rate) / sero_rate;
+      const double hi = pweibull_lower((double)(v + 1) - sq, shape, scale), lo = pweibull_lower(fmax((double)v - sq, 0.0), shape, scale);
+      acc = fma(0.5 * wq * f, hi - lo, acc);
+    }
+  }
+  pi[idx] = acc;
+}
+
+// lam[c * T + r] (r >= c) = sum_{t <= c} inf[t] pi(c - t, r - t); lam_never[c] = mu_s[c] - sum_r lam[c][r].  One thread per (c, r).
+__global__ void sim_serorev_means_kernel(const double* __restrict__ inf, const double* __restrict__ pi, int T, double* __restrict__ lam) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * T) return;
+  const int c = (int)(idx / T), r = (int)(idx - (long long)c * T);
+  double a = 0.0;
+  if (r >= c)
+    for (int t = 0; t <= c; t++) a = fma(inf[t], pi[(long long)(c - t) * T + (r - t)], a);
+  lam[idx] = a;
+}
+
+// one thread per (replicate, c, stratum): everybody who converts on day c, split by reversion day (r = c .. T-1, or not
+// within the study).  The daily conversions are the sum of the cells (overwriting the count drawn without reversion), the
+// daily reversions are accumulated with atomics (exact: the counts are integers far below 2^53).
+__global__ void sim_serorev_draw_kernel(const double* __restrict__ lam, const double* __restrict__ mu_s, const double* __restrict__ w_sero,
+                                        int T, int A, long long n_rep, unsigned long long seed, double* __restrict__ serocon,
+                                        double* __restrict__ serorev) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cells = (long long)T * A;
+  if (idx >= n_rep * cells) return;
+  const long long rep = idx / cells;
+  const int cell = (int)(idx - rep * cells), c = cell / A, a = cell - c * A;
+  SimRng g{seed, (uint32_t)rep, (uint32_t)cell, 2u, 0u, {0, 0, 0, 0}, 0};
+  const double wa = w_sero[a];
+  double tot = 0.0, lsum = 0.0;
+  for (int r = c; r < T; r++) {
+    const double l = lam[(long long)c * T + r];
+    lsum += l;
+    const double n = rpois_dev(l * wa, g);
+    if (n > 0.0) {
+      tot += n;
+      atomicAdd(&serorev[(rep * T + r) * A + a], n);
+    }
+  }
+  tot += rpois_dev(fmax(mu_s[c] - lsum, 0.0) * wa, g);
+  serocon[idx] = tot;
 }
 
 }  // namespace ccdev

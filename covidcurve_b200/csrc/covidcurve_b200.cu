@@ -1660,13 +1660,17 @@ extern "C" int cc_dmma_probe(int device, int iters, int fma_per_mma, double* mma
 // ------------------------------------------------------------------------------------------------ forward simulator
 extern "C" int cc_simulate_infxn_2_death(int device, const double* infections, int32_t T, const double* ifr, const double* rho,
                                          const double* popN, int32_t A, double m_od, double s_od, double sero_delay_rate,
-                                         double smplfrac, uint64_t seed, int64_t n_rep, double* deaths, double* serocon,
-                                         double* mean_deaths, double* mean_serocon) {
+                                         double smplfrac, double sero_rev_shape, double sero_rev_scale, uint64_t seed, int64_t n_rep,
+                                         double* deaths, double* serocon, double* serorev, double* mean_deaths, double* mean_serocon) {
   if (!infections || !ifr || !rho || !popN) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: null argument");
   if (T < 1 || A < 1 || n_rep < 0) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: need T >= 1, A >= 1, n_rep >= 0");
   if (n_rep > 0 && (!deaths || !serocon)) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: null output");
   if (!(m_od > 0.0) || !(s_od > 0.0) || !(sero_delay_rate > 0.0) || !(smplfrac > 0.0) || !(smplfrac <= 1.0))
     return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: m_od, s_od, sero_delay_rate must be positive and smplfrac in (0, 1]");
+  const bool rev = (sero_rev_shape != 0.0) || (sero_rev_scale != 0.0);
+  if (rev && (!(sero_rev_shape > 0.0) || !(sero_rev_scale > 0.0) || (n_rep > 0 && !serorev)))
+    return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: seroreversion needs shape > 0, scale > 0 and the serorev output");
+  if (rev && T > 2048) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: seroreversion supports up to 2048 days");
   if ((long long)n_rep * T * A > (1LL << 40)) return fail(CC_E_INVALID, "cc_simulate_infxn_2_death: too many cells");
   if (cc_device_count() <= 0) return fail(CC_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
   double wsum = 0.0;
@@ -1686,11 +1690,12 @@ extern "C" int cc_simulate_infxn_2_death(int device, const double* infections, i
     ws[a] = pa * smplfrac;
   }
   CC_CUDA(cudaSetDevice(device));
-  const size_t cells = (size_t)T * A, tot = (size_t)n_rep * cells;
+  const size_t cells = (size_t)T * A, tot = (size_t)n_rep * cells, tot1 = std::max<size_t>(tot, 1);
+  const size_t tt = rev ? (size_t)T * T : 0;
   double* d = nullptr;
-  CC_CUDA(cudaMalloc((void**)&d, ((size_t)5 * T + 2 * A + 2 * std::max<size_t>(tot, 1)) * sizeof(double)));
+  CC_CUDA(cudaMalloc((void**)&d, ((size_t)5 * T + 2 * A + (rev ? 3 : 2) * tot1 + 2 * tt) * sizeof(double)));
   double *d_inf = d, *d_dG = d + T, *d_dH = d + 2 * T, *d_mud = d + 3 * T, *d_mus = d + 4 * T, *d_wd = d + 5 * T, *d_ws = d_wd + A,
-         *d_deaths = d_ws + A, *d_sero = d_deaths + std::max<size_t>(tot, 1);
+         *d_deaths = d_ws + A, *d_sero = d_deaths + tot1, *d_rev = d_sero + tot1, *d_pi = d_rev + (rev ? tot1 : 0), *d_lam = d_pi + tt;
   cudaError_t e = cudaMemcpy(d_inf, infections, (size_t)T * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_wd, wd.data(), (size_t)A * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_ws, ws.data(), (size_t)A * sizeof(double), cudaMemcpyHostToDevice);
@@ -1702,8 +1707,21 @@ extern "C" int cc_simulate_infxn_2_death(int device, const double* infections, i
     sim_draw_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(d_mud, d_mus, d_wd, d_ws, T, A, (long long)n_rep, seed, d_deaths, d_sero);
     e = cudaGetLastError();
   }
+  if (e == cudaSuccess && rev) {
+    sim_serorev_pi_kernel<<<(unsigned)((tt + 255) / 256), 256>>>(T, sero_delay_rate, sero_rev_shape, sero_rev_scale, d_pi);
+    sim_serorev_means_kernel<<<(unsigned)((tt + 255) / 256), 256>>>(d_inf, d_pi, T, d_lam);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && tot > 0) {
+      e = cudaMemset(d_rev, 0, tot * sizeof(double));
+      if (e == cudaSuccess) {
+        sim_serorev_draw_kernel<<<(unsigned)((tot + 127) / 128), 128>>>(d_lam, d_mus, d_ws, T, A, (long long)n_rep, seed, d_sero, d_rev);
+        e = cudaGetLastError();
+      }
+    }
+  }
   if (e == cudaSuccess && tot > 0) e = cudaMemcpy(deaths, d_deaths, tot * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && tot > 0) e = cudaMemcpy(serocon, d_sero, tot * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tot > 0 && rev) e = cudaMemcpy(serorev, d_rev, tot * sizeof(double), cudaMemcpyDeviceToHost);
   std::vector<double> mud, mus;
   if (e == cudaSuccess && (mean_deaths || mean_serocon)) {
     mud.resize(T); mus.resize(T);

@@ -4,7 +4,8 @@ directly on the device as the independent Poisson variables they are, instead of
 infection (csrc/cc_sim.cuh explains the equivalence).  A cfg4-size epidemic (millions of infections) costs the same as a
 small one.  Differences, all deliberate:
   * `return_linelist = TRUE` is not available (there is no line list);
-  * `simulate_seroreversion = TRUE` is not available: reversion couples two event days of one person;
+  * with `simulate_seroreversion = TRUE` the conversion and reversion day of a person are coupled, so the independent
+    Poisson cells are the (conversion day, reversion day) pairs (csrc/cc_sim.cuh);
   * random numbers come from the device's counter-based generator (`seed`), not from R's stream.
 """
 from __future__ import annotations
@@ -34,14 +35,16 @@ def Agesim_infxn_2_death(fatalitydata, infections, m_od=14.26, s_od=0.79, curr_d
             raise ValueError("%s must be in [0, 1]" % name)
     if not (0 < smplfrac <= 1):
         raise ValueError("smplfrac must be in (0, 1]")
-    if simulate_seroreversion:
-        raise NotImplementedError("seroreversion is not simulated by the aggregate sampler (see module docstring)")
+    if simulate_seroreversion and (sero_rev_shape is None or sero_rev_scale is None or not (sero_rev_shape > 0 and sero_rev_scale > 0)):
+        raise ValueError("sero_rev_shape and sero_rev_scale must be positive numbers when simulate_seroreversion is TRUE")
     if return_linelist:
         raise NotImplementedError("the aggregate sampler has no line list")
     T, strata = int(curr_day), list(fatalitydata["Strata"])
     A = len(strata)
     sim = _lib.simulate_infxn_2_death(infections, fatalitydata["IFR"].to_numpy(), fatalitydata["Rho"].to_numpy(),
-                                      demog["popN"].to_numpy(), m_od, s_od, sero_delay_rate, smplfrac, seed=seed, n_rep=1, device=device)
+                                      demog["popN"].to_numpy(), m_od, s_od, sero_delay_rate, smplfrac, seed=seed, n_rep=1, device=device,
+                                      sero_rev_shape=sero_rev_shape if simulate_seroreversion else None,
+                                      sero_rev_scale=sero_rev_scale if simulate_seroreversion else None)
     deaths, conv = sim["deaths"][0], sim["serocon"][0]                       # [T][A]
     days = np.arange(1, T + 1)
     death_strata = pd.DataFrame({"ObsDay": np.repeat(days, A).astype(float), "Strata": pd.Categorical(strata * T, categories=strata),
@@ -50,7 +53,9 @@ def Agesim_infxn_2_death(fatalitydata, infections, m_od=14.26, s_od=0.79, curr_d
     tested = demog["popN"].to_numpy(dtype=np.float64) * smplfrac             # simulators.R:57-58
     cum = np.cumsum(conv, axis=0)                                            # TrueSeroCount = cumulative seroconversions
     true_prev = cum / tested[None, :]
-    obs_prev = sens * true_prev + (1 - spec) * (1 - true_prev)               # simulators.R:81-84 (no reversion)
+    still = cum - (np.cumsum(sim["serorev"][0], axis=0) if simulate_seroreversion else 0.0)   # RevertSeroCount, simulators.R:80
+    obs_prev = still / tested[None, :]
+    obs_prev = sens * obs_prev + (1 - spec) * (1 - obs_prev)                  # simulators.R:82-84
     # the reference groups by Strata, then day
     sero = pd.DataFrame({"Strata": np.repeat(np.array(strata, dtype=object), T), "ObsDay": np.tile(days, A).astype(float),
                          "testedN": np.repeat(tested, T), "TrueSeroCount": cum.T.reshape(-1).astype(np.int64),

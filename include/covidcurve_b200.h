@@ -222,13 +222,17 @@ int cc_nmath_batch(int device, int fn, const double* a, const double* b, const d
  *   deaths[r][j][a]  ~ Poisson(P_a ifr_a    sum_{t<=j} infections[t] (G(j-t+1) - G(j-t))),  G = gamma(1/s_od^2, m_od s_od^2) cdf
  *   serocon[r][j][a] ~ Poisson(P_a smplfrac sum_{t<=j} infections[t] (H(j-t+1) - H(j-t))),  H = exponential cdf, mean sero_delay_rate
  * with P_a = popN_a rho_a / sum(popN rho).  `deaths`, `serocon`: host arrays [n_rep][T][A] (daily counts; the caller
- * accumulates).  `mean_deaths`, `mean_serocon`: optional host arrays [T][A] of the cell means.  Seroreversion is not
- * simulated.  Random numbers: Philox keyed by (seed, replicate, cell); parity with R's stream is distributional only.
+ * accumulates).  `mean_deaths`, `mean_serocon`: optional host arrays [T][A] of the cell means.
+ * Seroreversion (sim_seroprev, R/simulators.R:26-33): with sero_rev_shape > 0 and sero_rev_scale > 0 the time from
+ * seroconversion to reversion is Weibull; conversions and reversions are then drawn jointly as Poisson cells over the pairs
+ * (conversion day, reversion day) and `serorev` [n_rep][T][A] receives the daily reversions among the sampled people
+ * (pass shape = scale = 0 and serorev = NULL for no reversion).
+ * Random numbers: Philox keyed by (seed, replicate, cell); parity with R's stream is distributional only.
  * --------------------------------------------------------------------------------------------------------- */
 int cc_simulate_infxn_2_death(int device, const double* infections, int32_t T, const double* ifr, const double* rho,
                               const double* popN, int32_t A, double m_od, double s_od, double sero_delay_rate, double smplfrac,
-                              uint64_t seed, int64_t n_rep, double* deaths, double* serocon, double* mean_deaths,
-                              double* mean_serocon);
+                              double sero_rev_shape, double sero_rev_scale, uint64_t seed, int64_t n_rep, double* deaths,
+                              double* serocon, double* serorev, double* mean_deaths, double* mean_serocon);
 #define CC_FN_RPOIS 11 /* test hook: one Poisson draw, a = mean, b = replicate id, c = seed */
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -148,7 +148,7 @@ def test_simulator_mirror_validates_like_the_reference():
         simulators.Agesim_infxn_2_death(fat, inf, **dict(kw, spec=1.5))
     with pytest.raises(ValueError, match="smplfrac"):
         simulators.Agesim_infxn_2_death(fat, inf, smplfrac=0.0, **kw)
-    with pytest.raises(NotImplementedError):
-        simulators.Agesim_infxn_2_death(fat, inf, simulate_seroreversion=True, sero_rev_shape=3.0, sero_rev_scale=140.0, **kw)
+    with pytest.raises(ValueError, match="sero_rev_shape"):
+        simulators.Agesim_infxn_2_death(fat, inf, simulate_seroreversion=True, sero_rev_shape=None, sero_rev_scale=140.0, **kw)
     with pytest.raises(NotImplementedError):
         simulators.Agesim_infxn_2_death(fat, inf, return_linelist=True, **kw)

@@ -93,8 +93,46 @@ def test_Agesim_infxn_2_death_mirror(built_lib):
     P = demog["popN"].to_numpy() / demog["popN"].sum()
     want = np.convolve(infxns, np.diff(G))[:T].sum() * (P * fat["IFR"].to_numpy()).sum()
     assert abs(agg["Deaths"].sum() - want) < 5 * np.sqrt(want)
-    with pytest.raises(NotImplementedError):
-        simulators.Agesim_infxn_2_death(fat, infxns, curr_day=T, spec=0.95, sens=0.85, demog=demog, sero_delay_rate=18.3,
-                                        simulate_seroreversion=True, sero_rev_shape=3, sero_rev_scale=140)
+    rev = simulators.Agesim_infxn_2_death(fat, infxns, m_od=19.8, s_od=0.85, curr_day=T, spec=0.95, sens=0.85, demog=demog,
+                                          sero_delay_rate=18.3, simulate_seroreversion=True, sero_rev_shape=3, sero_rev_scale=140,
+                                          smplfrac=1e-3, seed=5)["StrataAgg_Seroprev"]
+    assert np.all(rev["ObsPrev"] <= 0.85 * rev["TruePrev"] + 0.05 * (1 - rev["TruePrev"]) + 1e-15)   # reversions only lower it
+    assert np.any(rev["ObsPrev"] < 0.85 * rev["TruePrev"] + 0.05 * (1 - rev["TruePrev"]) - 1e-12)    # and somebody did revert
     with pytest.raises(ValueError):
         simulators.Agesim_infxn_2_death(fat, infxns[:-1], curr_day=T, spec=0.95, sens=0.85, demog=demog, sero_delay_rate=18.3)
+
+
+def test_seroreversion_cells(built_lib):
+    """Joint (conversion day, reversion day) cells: nobody reverts before converting, and the expected cumulative
+    reversions equal the line-list model's  sum_t inf[t] w_a P(Exp + Weibull <= j - t + 1)."""
+    from scipy import integrate, stats
+    from covidcurve_b200 import _lib
+    T, A = 120, 2
+    t = np.arange(1, T + 1)
+    infections = 3000.0 / (1 + np.exp(-(t - 40) / 6.0))
+    ifr, rho, pop = np.array([0.01, 0.1]), np.array([1.0, 1.0]), np.array([3e5, 1e5])
+    rate, shape, scale, frac = 12.0, 2.5, 60.0, 0.5
+    R = 300
+    sim = _lib.simulate_infxn_2_death(infections, ifr, rho, pop, 14.26, 0.79, rate, frac, seed=3, n_rep=R, sero_rev_shape=shape,
+                                      sero_rev_scale=scale)
+    conv, rev = np.cumsum(sim["serocon"], axis=1), np.cumsum(sim["serorev"], axis=1)
+    assert np.all(rev <= conv) and np.all(sim["serorev"] >= 0) and rev[:, -1].sum() > 0
+    # conversions keep their marginal law
+    mu_c = sim["mean_serocon"]
+    z = (sim["serocon"].mean(axis=0) - mu_c) / np.sqrt(np.maximum(mu_c, 1e-12) / R)
+    assert np.abs(z[mu_c > 0.05]).max() < 5.5
+    ratio = sim["serocon"].var(axis=0, ddof=1)[mu_c > 5] / mu_c[mu_c > 5]
+    assert abs(ratio.mean() - 1) < 0.03
+    # expected cumulative reversions by day j
+    cdf = lambda x: integrate.quad(lambda s: np.exp(-s / rate) / rate * stats.weibull_min.cdf(x - s, shape, scale=scale), 0, x)[0]
+    F = np.array([cdf(float(k)) for k in range(T + 1)])
+    w = pop * rho / (pop * rho).sum() * frac
+    for j in (60, 90, 120):
+        want = sum(infections[tt - 1] * F[j - tt + 1] for tt in range(1, j + 1)) * w
+        got = rev[:, j - 1, :].mean(axis=0)
+        se = np.sqrt(want / R)
+        assert np.all(np.abs(got - want) < 5 * se + 1e-9), (j, got, want)
+    # reproducible
+    again = _lib.simulate_infxn_2_death(infections, ifr, rho, pop, 14.26, 0.79, rate, frac, seed=3, n_rep=2, sero_rev_shape=shape,
+                                        sero_rev_scale=scale)
+    assert np.array_equal(again["serorev"], sim["serorev"][:2]) and np.array_equal(again["serocon"], sim["serocon"][:2])
