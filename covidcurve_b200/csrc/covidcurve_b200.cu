@@ -1394,6 +1394,9 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
         cc_mcmc_destroy(r);
         return fail(CC_E_INVALID, "model too large for the shared memory of the Metropolis sweep kernel");
       }
+      // fewer particles than resident warp slots: thinner CTAs, so that every SM gets its share
+      const long long per_sm = ((long long)P + (long long)best_ctas * m->sm_count - 1) / ((long long)best_ctas * m->sm_count);
+      if (per_sm < best_wpc) best_wpc = (int)std::max<long long>(1, per_sm);
       r->sweep_wpc = best_wpc;
       r->sweep_smem = per_warp * best_wpc;
       r->sweep_grid = (unsigned)std::min<long long>(((long long)P + best_wpc - 1) / best_wpc, (long long)best_ctas * m->sm_count);
