@@ -91,15 +91,14 @@ __host__ __device__ constexpr int p2_ctas(int nt) { return nt <= 7 ? 2 : 1; }
 #endif
 constexpr int kSweepWarps = CC_SWEEP_WARPS;
 
-// ---- batched likelihood as a two-pass pipeline --------------------------------------------------------------------
+// ---- batched likelihood as a four-pass pipeline (five launches) -------------------------------------------------------
 // pass A (one THREAD per vector): phase 1 -> record rec[f * cap + v] in global memory, a regime key, a histogram of the keys
-// pass B (tiny): bucket offsets, then a scatter that groups the vector indices by key (order within a bucket is irrelevant:
-//         every vector is evaluated independently, so the values do not depend on the permutation)
-// pass C (one WARP per vector, tiles of 32 positions of the permutation): phase 2, the per-day work.
+// pass B (tiny, two launches): bucket offsets, then a scatter that groups the vector indices by key (order within a bucket is
+//         irrelevant: every vector is evaluated independently, so the values do not depend on the permutation)
+// pass C (one WARP per vector, CTA tiles of the permutation drawn from a ticket): phase 2, the per-day work.
 // pass D (one THREAD per vector): phase 3.
-// Grouping by regime keeps the warps of an SM on the same code path (small gamma table / large table / general algorithm /
-// no per-day work at all), which is what keeps the instruction cache warm on heterogeneous batches: measured 37 -> see
-// profiles/r1_summary.md M evals/s on box-uniform vectors.
+// Grouping by regime keeps the warps of a CTA on the same code path (small gamma table / large table / general algorithm /
+// no per-day work at all) and lets the launch start with the expensive vectors (history: profiles/r1_summary.md).
 constexpr int kNumKeys = 8;       // histogram slots; keys 0..5 are used, slot 6 is the phase-2 tile ticket
 constexpr int kPhase2Tile = 8;    // vectors per dynamically fetched tile of pass C
 
@@ -1048,7 +1047,7 @@ static int ensure_work(cc_model* m, int slot, long long n) {
   return CC_OK;
 }
 
-// the batched likelihood: pass A (thread per vector) -> regime buckets -> pass C (warp per vector); 4 launches on one stream
+// the batched likelihood: pass A (thread per vector) -> regime buckets -> pass C (warp per vector) -> pass D; 5 launches on one stream
 static int launch_loglike(cc_model* m, const double* d_theta, long long n, long long ld, double* d_out, cudaStream_t st, int slot) {
   const KModel& k = m->k;
   if (n > 0x7fffffffLL) return fail(CC_E_INVALID, "batch too large (2^31 vectors per call)");
