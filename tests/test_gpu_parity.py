@@ -169,6 +169,41 @@ def test_full_size_linearity_property(built_lib):
     assert relerr(ll[sub], _oracle(spec).loglike(th[sub], nthreads=8)) <= TOL
 
 
+def test_baseline_size_batch_properties(built_lib):
+    """BASELINE.json cfg5 at its full size (2^20 box-uniform vectors): the value of a vector does not depend on how the
+    batch is cut - one device launch, two half launches, the host-buffer path with its geometric chunks on two streams and
+    the reversed batch all agree bit for bit - and a random subset agrees with the oracle."""
+    import torch
+    from covidcurve_b200 import _lib, synth
+    spec, truth = synth.make_spec("cfg3")
+    n = 1 << 20
+    th = synth.random_theta(spec, n, seed=synth.SEED_THETA, bad_frac=0.01)
+    m = _model(spec)
+    soa = np.ascontiguousarray(th.T)
+    host = m.loglike(th)                                              # host buffers: chunks of 64k .. 512k vectors
+    d_th = torch.from_numpy(soa).cuda()
+    d_out = torch.empty(n, dtype=torch.float64, device="cuda")
+    m.loglike_ptr(d_th.data_ptr(), n, n, d_out.data_ptr(), _lib.CC_MEM_DEVICE, 0)
+    torch.cuda.synchronize()
+    one = d_out.cpu().numpy()
+    assert np.array_equal(one, host)
+    h = n // 2 + 12345                                                # two ragged launches into the same output
+    d_out.zero_()
+    m.loglike_ptr(d_th.data_ptr(), h, n, d_out.data_ptr(), _lib.CC_MEM_DEVICE, 0)
+    m.loglike_ptr(d_th.data_ptr() + 8 * h, n - h, n, d_out.data_ptr() + 8 * h, _lib.CC_MEM_DEVICE, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), one)
+    assert np.array_equal(m.loglike(th[::-1])[::-1], one)
+    fail = one == -np.finfo(float).max / 100
+    assert 0.02 < fail.mean() < 0.06 and np.isfinite(one).all()       # the 1 % bad slice + population-check failures
+    sub = np.random.default_rng(1).choice(n, 2000, replace=False)
+    # DESIGN.md section 2, known residual: for sod in [0.0214, 0.0232] an expected-death value sits within one or two quanta of
+    # the smallest subnormal and the reference's own result hangs on the last bit of its libm; those vectors are not compared
+    sod = th[sub, spec.index("sod")]
+    sub = sub[~((sod > 0.021) & (sod < 0.0235))]
+    assert len(sub) > 1900 and relerr(one[sub], _oracle(spec).loglike(th[sub], nthreads=8)) <= TOL
+
+
 def test_curves_match_oracle_intermediates(built_lib, modfit):
     spec, g = modfit
     m, o = _model(spec), _oracle(spec)
