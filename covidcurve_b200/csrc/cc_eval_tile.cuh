@@ -97,6 +97,15 @@ __device__ __noinline__ double pgamma_lower_shared(const GammaShape& g, double x
 // Scalar-per-vector pieces.  `par(i)` returns parameter i of the vector, `put(f, v)` stores record field f.
 // The pieces are independent so that the Metropolis step can redo only what a single-parameter proposal touches.
 
+// IFR of stratum a with the re-parameterisation lift (the value p1_weights multiplies into ne*ma)
+template <typename Par>
+__device__ __forceinline__ double ifr_of(const KModel& m, Par par, int a) {
+  const int r = m.idx_ifr[a];
+  double ma = par(r);
+  if (m.reparam_ifr && r != m.idx_max_ma) ma = ma * par(m.idx_max_ma);
+  return ma;
+}
+
 // attack-rate weights (binomial.cpp:60-73), ne*ma, test characteristics
 template <typename Par, typename Put>
 __device__ inline void p1_weights(const KModel& m, const RecLayout& L, Par par, Put put) {
@@ -382,13 +391,9 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
       if (E > -690.0 || !(alph > 1.0)) {
         pv = exp(E) * ssum;
       } else {
-        // Gradual-underflow regime: the reference forms P = pd_upper * dpois_wrap with dpois_wrap = exp(.) / sqrt(2 pi (a-1))
-        // (R nmath dpois_raw), and the subnormal exp(.) carries only a few bits.  Round at the same places so that the
-        // quantised value is the reference's (the operands agree to ~1e-12, the subnormal grid is ~1e-4 wide).
-        const double am1 = alph - 1.0;
-        const double t1 = exp_gradual(E - lx + log(alph) + 0.5 * log(CC_2PI * am1));  // = exp(-stirlerr(a-1) - bd0(a-1, x))
-        const double dd = t1 / sqrt(CC_2PI * am1);
-        pv = ((x / alph) * ssum) * dd;
+        // Below DBL_MIN / DBL_EPSILON R's pgamma_raw recomputes the value in log space and applies ONE exp, so a subnormal
+        // result is rounded once, from the exact value: do the same (log P = E + log(series))
+        pv = exp_gradual(E + log(ssum));
       }
       if (k <= km) P[k] = pv;
     }
@@ -567,8 +572,34 @@ __device__ inline void stage_conv(const KModel& m, const double* __restrict__ xs
   double auc[NT][2];
   nb = __shfl_sync(0xffffffffu, nb, 0);  // warp-uniform by construction; tell the compiler so (uniform loop exits around the MMAs)
   toeplitz_dmma<NT>(xs, gs, nb, auc);
-  __syncwarp();  // aucs may alias the kernel region
   const int n = lane >> 2, t = lane & 3;
+  {
+    // Where an output is (near) subnormal the reference's value is decided by gradual underflow: it rounds every product
+    // infxn[i] * dg[j - i] to the subnormal grid and adds them in the order i = 0, 1, ... (binomial.cpp:187-193), while the
+    // tensor-core accumulation keeps the products exact.  Redo exactly those outputs the reference's way (early days of
+    // very peaked delay distributions; a handful of terms each).  An exact zero needs no redo (every product is zero in
+    // both), and above 1e-300 a rounding of 2.5e-324 per term is below 1e-23 of the sum.
+    const double kTiny = 1e-300;
+    bool tiny = false;
+#pragma unroll
+    for (int P = 0; P < NT; P++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) tiny |= (64 * P + 16 * t + 8 * e + n < m.T) && (fabs(auc[P][e]) < kTiny) && (auc[P][e] != 0.0);
+    if (__any_sync(0xffffffffu, tiny)) {
+#pragma unroll
+      for (int P = 0; P < NT; P++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int j = 64 * P + 16 * t + 8 * e + n;
+          if (j < m.T && fabs(auc[P][e]) < kTiny && auc[P][e] != 0.0) {
+            double sref = 0.0;
+            for (int i = 0; i <= j; i++) sref = __dadd_rn(sref, __dmul_rn(xs[xs_index(i)], gs[7 + j - i]));
+            auc[P][e] = sref;
+          }
+        }
+    }
+  }
+  __syncwarp();  // aucs may alias the kernel region
 #pragma unroll
   for (int P = 0; P < NT; P++) {
     aucs[64 * P + 16 * t + n] = auc[P][0];
@@ -579,8 +610,12 @@ __device__ inline void stage_conv(const KModel& m, const double* __restrict__ xs
 
 // ---- S8 Poisson term, evaluated day by day (binomial.cpp:199-221): l1 (without the data-only constant), sum of expd over
 // all days, sum of auc over the uncensored days
-__device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, const double* __restrict__ aucs, double snm, double& l1,
-                                       double& s_all, double& s_unc) {
+// `ne` (attack-rate weights) and `par` (the parameter vector) are read only for days whose expected count is zero or
+// subnormal: there the reference's own sum  sum_a (auc * ne[a]) * ma[a]  (binomial.cpp:209-212, every product rounded to the
+// subnormal grid) decides the value, not auc * sum_a ne[a] ma[a].
+template <typename Par>
+__device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, const double* __restrict__ aucs, double snm,
+                                       const double* __restrict__ ne, Par par, double& l1, double& s_all, double& s_unc) {
   const int lane = threadIdx.x & 31, T = m.T;
   double dummy = 0.0;
   l1 = s_all = s_unc = 0.0;
@@ -603,9 +638,14 @@ __device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, co
     // some observed day has a zero / subnormal / negative / non-finite mean or a negative count: R's case analysis
     l1 = 0.0;
     for (int j = lane; j < T; j += 32) {
-      const double expd = aucs[j] * snm;
+      double expd = aucs[j] * snm;
       const int x = tb.obsd[j];
       if ((j + 1) < m.rcensor_day && x != -1) {
+        if (expd >= 0.0 && expd < DBL_MIN && aucs[j] != 0.0) {  // (would-be) subnormal: the reference's operation order
+          const double a = aucs[j];
+          expd = 0.0;
+          for (int q = 0; q < m.A; q++) expd = __dadd_rn(expd, __dmul_rn(__dmul_rn(a, ne[q]), ifr_of(m, par, q)));
+        }
         double lp;
         if (!(expd >= 0.0)) lp = d_nan();        // NaN or negative mean -> NaN (R::dpois)
         else if (x < 0) lp = -d_inf();
@@ -667,9 +707,9 @@ __device__ inline void stage_surveys(const KModel& m, const double* __restrict__
 }
 
 // phase 2 for vector e of the tile: per-day stages; writes o_status, o_l1, o_texpd, o_sunc, o_base[S] to the scratch
-template <int NT>
+template <int NT, typename Par>
 __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr, int e,
-                                   long long stride = 32) {
+                                   Par par, long long stride = 32) {
   const int lane = threadIdx.x & 31, T = m.T;
   __syncwarp();
   for (int f = lane; f < L.n2; f += 32) w.rec[f] = scr[f * stride + e];
@@ -694,7 +734,7 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
     }
   }
   double l1, s_all, s_unc;
-  stage_l1_direct(m, tb, w.auc, w.rec[L.snm], l1, s_all, s_unc);
+  stage_l1_direct(m, tb, w.auc, w.rec[L.snm], w.rec + L.ne, par, l1, s_all, s_unc);
   if (lane == 0) {
     scr[L.o_l1 * stride + e] = l1 - m.l1_const;
     scr[L.o_texpd * stride + e] = s_all;

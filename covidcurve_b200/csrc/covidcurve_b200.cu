@@ -156,9 +156,9 @@ __global__ void bucket_scatter_kernel(const int* __restrict__ key, long long n, 
 
 // tile_phase2 with a CTA barrier in front of every stage: all warps of the CTA execute the same stage code at the same
 // time, so the SM fetches one instruction stream per CTA instead of one per warp.  `live` = this warp has a vector.
-template <int NT>
-__device__ __forceinline__ void cta_phase2(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr,
-                                           long long stride, bool live) {
+template <int NT, typename Par>
+__device__ __forceinline__ void cta_phase2_impl(const KModel& m, const RecLayout& L, const TileSmem& w, const TileTables& tb, double* __restrict__ scr,
+                                                long long stride, bool live, Par par) {
   const int lane = threadIdx.x & 31;
   __syncthreads();
   if (live) {
@@ -182,7 +182,7 @@ __device__ __forceinline__ void cta_phase2(const KModel& m, const RecLayout& L, 
   __syncthreads();
   if (live) {
     double l1, s_all, s_unc;
-    stage_l1_direct(m, tb, w.auc, w.rec[L.snm], l1, s_all, s_unc);
+    stage_l1_direct(m, tb, w.auc, w.rec[L.snm], w.rec + L.ne, par, l1, s_all, s_unc);
     if (lane == 0) {
       scr[L.o_l1 * stride] = l1 - m.l1_const;
       scr[L.o_texpd * stride] = s_all;
@@ -195,7 +195,8 @@ __device__ __forceinline__ void cta_phase2(const KModel& m, const RecLayout& L, 
 template <int NT>
 __global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2_kernel(const KModel m, long long n, double* __restrict__ rec,
                                                                                           long long cap, const int* __restrict__ perm,
-                                                                                          unsigned int* __restrict__ ticket) {
+                                                                                          unsigned int* __restrict__ ticket,
+                                                                                          const double* __restrict__ theta, long long ld) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned int s_ticket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,14 +220,14 @@ __global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2
     for (int e = 0; e < kPhase2Tile; e++) {
 #if CC_P2_SYNC == 2
       const long long v = __shfl_sync(0xffffffffu, vl, min(e, max(cnt - 1, 0)));
-      cta_phase2<NT>(m, L, w, tb, rec + v, cap, e < cnt);
+      cta_phase2_impl<NT>(m, L, w, tb, rec + v, cap, e < cnt, [&](int i) { return theta[(long long)i * ld + v]; });
 #else
 #if CC_P2_SYNC == 1
       __syncthreads();  // the warps of the CTA start every evaluation together
 #endif
       if (e < cnt) {
         const long long v = __shfl_sync(0xffffffffu, vl, e);
-        tile_phase2<NT>(m, L, w, tb, rec + v, (int)0, cap);
+        tile_phase2<NT>(m, L, w, tb, rec + v, (int)0, [&](int i) { return theta[(long long)i * ld + v]; }, cap);
       }
 #endif
     }
@@ -281,7 +282,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, CC_MIN_CTAS) mcmc_init_tile
     if (valid && tl.sub == 0) tile_phase1<NT>(m, L, scr, tl.e, par);
     __syncwarp();
     const int cnt = min(tl.E, P - p0);
-    for (int q = 0; q < cnt; q++) tile_phase2<NT>(m, L, w, tb, scr, q);
+    for (int q = 0; q < cnt; q++) {
+      const double* thq = s.theta + (size_t)(p0 + q) * d;
+      tile_phase2<NT>(m, L, w, tb, scr, q, [&](int j) { return thq[j]; });
+    }
     __syncwarp();
     const double ll = tile_phase3(m, L, scr, tl.e, tl.sub, tl.G, tl.E);
     const double lp = tile_logprior(m, tl.sub, tl.G, tl.E, par);
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
     const double snm = rec[L.snm];
     return q.irregular || !(snm > 0.0) || !isfinite(snm);
   };
-  auto finish_l1 = [&](double* rec, const L1Sums& q, const double* aucs) {
+  auto finish_l1 = [&](double* rec, const L1Sums& q, const double* aucs, auto parf) {
     const double snm = rec[L.snm];
     double l1, texpd;
     if (!l1_needs_days(rec, q)) {
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
       texpd = snm * q.s_all_auc;
     } else {
       double su;
-      stage_l1_direct(m, tb, aucs, snm, l1, texpd, su);
+      stage_l1_direct(m, tb, aucs, snm, rec + L.ne, parf, l1, texpd, su);
     }
     __syncwarp();
     if (lane == 0) {
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
             warp_copy(w.auc, cache + CL.auc, CL.nauc);
             __syncwarp();
           }
-          finish_l1(w.recB, sums_p, w.auc);
+          finish_l1(w.recB, sums_p, w.auc, par);
         }
       }
       __syncwarp();
@@ -1068,7 +1072,7 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
     loglike_phase1_kernel<NT_><<<gridA, 128, 0, st>>>(k, d_theta, n, ld, wk.rec, wk.cap, wk.key, counts);                     \
     bucket_offsets_kernel<<<1, 1, 0, st>>>(counts, cursor);                                                                   \
     bucket_scatter_kernel<<<gridA, 128, 0, st>>>(wk.key, n, cursor, wk.perm);                                                 \
-    loglike_phase2_kernel<NT_><<<gridC, 32 * p2_warps(NT_), smem / kWarpsPerCta * p2_warps(NT_), st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 6);                      \
+    loglike_phase2_kernel<NT_><<<gridC, 32 * p2_warps(NT_), smem / kWarpsPerCta * p2_warps(NT_), st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 6, d_theta, ld);                      \
     loglike_phase3_kernel<<<gridA, 128, 0, st>>>(k, n, wk.rec, wk.cap, d_out);                                                \
     break;
     CC_FOR_EACH_NT(CC_LAUNCH)

@@ -351,6 +351,13 @@ __device__ __forceinline__ double pgamma_lower(const GammaShape& g, double x) {
       sum += term;
     } while (term > sum * DBL_EPSILON);
     res = sum * dpois_wrap(g, x);
+    // R's pgamma_raw redoes results below DBL_MIN / DBL_EPSILON (1.002e-292) in log space - exp(log(sum) + dpois_wrap(.., log))
+    // - because the product above loses its bits to gradual underflow.  Only this branch can get that small for a lower tail
+    // with shape > 1 (the small-x branch would need x < 1 << alph, i.e. a scale > 1 day with a huge shape: not both).
+    if (res < DBL_MIN / DBL_EPSILON && alph > 1 && isfinite(x)) {
+      const double dlog = -0.5 * log(CC_2PI * g.am1) + (-g.stir_am1 - bd0(g.am1, x));  // dpois_raw(alph - 1, x, log = TRUE)
+      res = exp_gradual(log(sum) + dlog);
+    }
   } else if (alph - 1 < x && alph < 0.8 * (x + 50)) {
     double d = dpois_wrap(g, x), sum;
     if (alph < 1) {
