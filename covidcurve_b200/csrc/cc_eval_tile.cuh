@@ -62,7 +62,7 @@ struct TileSmem {
   double* rec;  // [n2 rounded] record of the vector being processed
   double* xs;   // padded series
   double* gs;   // 7 zeros + delay kernel
-  double* auc;  // convolution output in day order (the batch kernels alias it onto gs + 8 once the kernel is consumed)
+  double* auc;  // convolution output in day order (the batch kernels alias it onto sk: the survey sums run before the convolution)
   double* sk;   // CH prefix sums
   double* ctab; // [128] interval-mass coefficients
 };
@@ -75,7 +75,7 @@ __device__ inline TileSmem carve_tile(double* q, const RecLayout& L, int NT) {
   w.rec = q; q += (L.n2 + 3) & ~3;
   w.xs = q; q += 12 * (8 * NT + 7);
   w.gs = q; q += 64 * NT + 16;
-  w.auc = w.gs + 8;
+  w.auc = q;  // = sk
   w.sk = q; q += 64 * NT + 4;
   w.ctab = q;
   return w;
@@ -552,6 +552,24 @@ __device__ inline bool stage_popn(const KModel& m, const RecLayout& L, const dou
   return __all_sync(0xffffffffu, ok);
 }
 
+// Where a convolution output is (near) subnormal the reference's value is decided by gradual underflow: it rounds every
+// product infxn[i] * dg[j - i] to the subnormal grid and adds them in the order i = 0, 1, ... (binomial.cpp:187-193), while
+// the tensor-core accumulation keeps the products exact.  Redo exactly those outputs the reference's way (early days of very
+// peaked delay distributions; a handful of terms each).  An exact zero needs no redo (every product is zero in both), and
+// above 1e-300 a rounding of 2.5e-324 per term is below 1e-23 of the sum.  Needs the series and the kernel still in place.
+__device__ __noinline__ void conv_fixup_tiny(int T, const double* __restrict__ xs, const double* __restrict__ gs, double* aucs) {
+  const int lane = threadIdx.x & 31;
+  for (int j = lane; j < T; j += 32) {
+    const double a = aucs[j];
+    if (a != 0.0 && fabs(a) < 1e-300) {
+      double sref = 0.0;
+      for (int i = 0; i <= j; i++) sref = __dadd_rn(sref, __dmul_rn(xs[xs_index(i)], gs[7 + j - i]));
+      aucs[j] = sref;
+    }
+  }
+  __syncwarp();
+}
+
 // ---- S7 death-delay convolution on the tensor cores, then back to day order through shared memory
 // Number of 8-day lag blocks of the delay kernel that can be non-zero.  Beyond x = alph + 9 sqrt(alph) + 45 the upper tail
 // is below 2^-54, every P value rounds to exactly 1 (in R as here) and the kernel masses are exactly zero, so the lag blocks
@@ -573,33 +591,7 @@ __device__ inline void stage_conv(const KModel& m, const double* __restrict__ xs
   nb = __shfl_sync(0xffffffffu, nb, 0);  // warp-uniform by construction; tell the compiler so (uniform loop exits around the MMAs)
   toeplitz_dmma<NT>(xs, gs, nb, auc);
   const int n = lane >> 2, t = lane & 3;
-  {
-    // Where an output is (near) subnormal the reference's value is decided by gradual underflow: it rounds every product
-    // infxn[i] * dg[j - i] to the subnormal grid and adds them in the order i = 0, 1, ... (binomial.cpp:187-193), while the
-    // tensor-core accumulation keeps the products exact.  Redo exactly those outputs the reference's way (early days of
-    // very peaked delay distributions; a handful of terms each).  An exact zero needs no redo (every product is zero in
-    // both), and above 1e-300 a rounding of 2.5e-324 per term is below 1e-23 of the sum.
-    const double kTiny = 1e-300;
-    bool tiny = false;
-#pragma unroll
-    for (int P = 0; P < NT; P++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) tiny |= (64 * P + 16 * t + 8 * e + n < m.T) && (fabs(auc[P][e]) < kTiny) && (auc[P][e] != 0.0);
-    if (__any_sync(0xffffffffu, tiny)) {
-#pragma unroll
-      for (int P = 0; P < NT; P++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int j = 64 * P + 16 * t + 8 * e + n;
-          if (j < m.T && fabs(auc[P][e]) < kTiny && auc[P][e] != 0.0) {
-            double sref = 0.0;
-            for (int i = 0; i <= j; i++) sref = __dadd_rn(sref, __dmul_rn(xs[xs_index(i)], gs[7 + j - i]));
-            auc[P][e] = sref;
-          }
-        }
-    }
-  }
-  __syncwarp();  // aucs may alias the kernel region
+  __syncwarp();
 #pragma unroll
   for (int P = 0; P < NT; P++) {
     aucs[64 * P + 16 * t + n] = auc[P][0];
@@ -613,9 +605,12 @@ __device__ inline void stage_conv(const KModel& m, const double* __restrict__ xs
 // `ne` (attack-rate weights) and `par` (the parameter vector) are read only for days whose expected count is zero or
 // subnormal: there the reference's own sum  sum_a (auc * ne[a]) * ma[a]  (binomial.cpp:209-212, every product rounded to the
 // subnormal grid) decides the value, not auc * sum_a ne[a] ma[a].
+// `fix_xs` / `fix_gs`: series and delay kernel of this evaluation if they are still in shared memory (else nullptr): the
+// rare path then first redoes the (near) subnormal convolution outputs the reference's way (conv_fixup_tiny).
 template <typename Par>
-__device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, const double* __restrict__ aucs, double snm,
-                                       const double* __restrict__ ne, Par par, double& l1, double& s_all, double& s_unc) {
+__device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, double* aucs, double snm, const double* __restrict__ ne,
+                                       Par par, double& l1, double& s_all, double& s_unc, const double* fix_xs = nullptr,
+                                       const double* fix_gs = nullptr) {
   const int lane = threadIdx.x & 31, T = m.T;
   double dummy = 0.0;
   l1 = s_all = s_unc = 0.0;
@@ -636,6 +631,7 @@ __device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, co
   }
   if (__any_sync(0xffffffffu, odd)) {
     // some observed day has a zero / subnormal / negative / non-finite mean or a negative count: R's case analysis
+    if (fix_xs) conv_fixup_tiny(m.T, fix_xs, fix_gs, aucs);
     l1 = 0.0;
     for (int j = lane; j < T; j += 32) {
       double expd = aucs[j] * snm;
@@ -723,24 +719,29 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   if (lane == 0) scr[L.o_status * stride + e] = ok ? 0.0 : 1.0;
   if (!ok) return;
   __syncwarp();
+  // the survey sums come first: they are the last readers of the hazard prefix sums, whose buffer then takes the convolution
+  // output - so the series and the delay kernel are still in place when the Poisson term needs them (rare subnormal path)
+  stage_surveys(m, w.xs, w.sk, [&](int s, double v) { scr[(L.o_base + s) * stride + e] = v; });
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
-    for (int j = lane; j < T; j += 32) m.debug_dump[j] = w.gs[7 + j];
+    for (int j = lane; j < T; j += 32) {
+      m.debug_dump[j] = w.gs[7 + j];
+      m.debug_dump[3 * T + j] = w.sk[min(j, m.M)];
+    }
+  __syncwarp();
   stage_conv<NT>(m, w.xs, w.gs, w.auc, conv_lag_blocks(m, L, w.rec));
+  double l1, s_all, s_unc;
+  stage_l1_direct(m, tb, w.auc, w.rec[L.snm], w.rec + L.ne, par, l1, s_all, s_unc, w.xs, w.gs);
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
     for (int j = lane; j < T; j += 32) {
       m.debug_dump[T + j] = w.xs[xs_index(j)];
       m.debug_dump[2 * T + j] = w.auc[j];
-      m.debug_dump[3 * T + j] = w.sk[min(j, m.M)];
     }
   }
-  double l1, s_all, s_unc;
-  stage_l1_direct(m, tb, w.auc, w.rec[L.snm], w.rec + L.ne, par, l1, s_all, s_unc);
   if (lane == 0) {
     scr[L.o_l1 * stride + e] = l1 - m.l1_const;
     scr[L.o_texpd * stride + e] = s_all;
     scr[L.o_sunc * stride + e] = s_unc;
   }
-  stage_surveys(m, w.xs, w.sk, [&](int s, double v) { scr[(L.o_base + s) * stride + e] = v; });
 }
 
 // ------------------------------------------------------------------------------------------------ phase 3

@@ -178,17 +178,18 @@ __device__ __forceinline__ void cta_phase2_impl(const KModel& m, const RecLayout
     __syncwarp();
   }
   __syncthreads();
+  if (live) stage_surveys(m, w.xs, w.sk, [&](int sv, double v) { scr[(L.o_base + sv) * stride] = v; });
+  __syncthreads();
   if (live) stage_conv<NT>(m, w.xs, w.gs, w.auc, conv_lag_blocks(m, L, w.rec));
   __syncthreads();
   if (live) {
     double l1, s_all, s_unc;
-    stage_l1_direct(m, tb, w.auc, w.rec[L.snm], w.rec + L.ne, par, l1, s_all, s_unc);
+    stage_l1_direct(m, tb, w.auc, w.rec[L.snm], w.rec + L.ne, par, l1, s_all, s_unc, w.xs, w.gs);
     if (lane == 0) {
       scr[L.o_l1 * stride] = l1 - m.l1_const;
       scr[L.o_texpd * stride] = s_all;
       scr[L.o_sunc * stride] = s_unc;
     }
-    stage_surveys(m, w.xs, w.sk, [&](int sv, double v) { scr[(L.o_base + sv) * stride] = v; });
   }
 }
 
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
     const double snm = rec[L.snm];
     return q.irregular || !(snm > 0.0) || !isfinite(snm);
   };
-  auto finish_l1 = [&](double* rec, const L1Sums& q, const double* aucs, auto parf) {
+  auto finish_l1 = [&](double* rec, const L1Sums& q, double* aucs, auto parf) {
     const double snm = rec[L.snm];
     double l1, texpd;
     if (!l1_needs_days(rec, q)) {
@@ -516,6 +517,10 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
             stage_conv<NT>(m, w.xs, w.gs, w.auc, conv_lag_blocks(m, L, w.recB));
             new_auc = true;
             sums_p = stage_l1_sums(m, tb, w.auc);
+            if (sums_p.irregular) {  // some expected count is not a positive normal number: the reference's subnormal arithmetic
+              conv_fixup_tiny(m.T, w.xs, w.gs, w.auc);
+              sums_p = stage_l1_sums(m, tb, w.auc);
+            }
           }
           if (need_surv) {
             if (!do_sero) {

@@ -199,6 +199,7 @@ struct GammaShape {  // everything that depends on alph only (one per parameter 
   double stir_a;       // stirlerr(alph)
   double rs2pi_am1;    // 1/sqrt(2 pi (alph-1))
   double rs2pi_a;      // 1/sqrt(2 pi alph)
+  double mhl2pi_am1;   // -0.5 log(2 pi (alph-1)) when alph > 1 (log form of the Poisson density)
 };
 
 __device__ __forceinline__ GammaShape gamma_shape(double alph) {
@@ -210,6 +211,7 @@ __device__ __forceinline__ GammaShape gamma_shape(double alph) {
   g.rs2pi_a = (alph > 0) ? rsqrt(CC_2PI * alph) : 0.0;
   g.stir_am1 = (alph > 1) ? stirlerr(alph - 1) : 0.0;
   g.rs2pi_am1 = (alph > 1) ? rsqrt(CC_2PI * (alph - 1)) : 0.0;
+  g.mhl2pi_am1 = (alph > 1) ? -0.5 * log(CC_2PI * (alph - 1)) : 0.0;
   return g;
 }
 
@@ -350,13 +352,16 @@ __device__ __forceinline__ double pgamma_lower(const GammaShape& g, double x) {
       term *= x / y;
       sum += term;
     } while (term > sum * DBL_EPSILON);
-    res = sum * dpois_wrap(g, x);
-    // R's pgamma_raw redoes results below DBL_MIN / DBL_EPSILON (1.002e-292) in log space - exp(log(sum) + dpois_wrap(.., log))
-    // - because the product above loses its bits to gradual underflow.  Only this branch can get that small for a lower tail
-    // with shape > 1 (the small-x branch would need x < 1 << alph, i.e. a scale > 1 day with a huge shape: not both).
-    if (res < DBL_MIN / DBL_EPSILON && alph > 1 && isfinite(x)) {
-      const double dlog = -0.5 * log(CC_2PI * g.am1) + (-g.stir_am1 - bd0(g.am1, x));  // dpois_raw(alph - 1, x, log = TRUE)
-      res = exp_gradual(log(sum) + dlog);
+    if (alph > 1 && isfinite(x)) {
+      // dpois_wrap(alph, x) = dpois_raw(alph - 1, x) in its main (saddle-point) form: for x >= 1 and alph > 1 none of its
+      // special cases applies.  The exponent is kept: R's pgamma_raw redoes results below DBL_MIN / DBL_EPSILON (1.002e-292)
+      // in log space - exp(log(sum) + dpois_wrap(.., log = TRUE)) - because the product loses its bits to gradual underflow.
+      // Only this branch can get that small for a lower tail with shape > 1.
+      const double arg = -g.stir_am1 - bd0(g.am1, x);
+      res = sum * (exp_gradual(arg) / sqrt(CC_2PI * g.am1));
+      if (res < DBL_MIN / DBL_EPSILON) res = exp_gradual(log(sum) + (g.mhl2pi_am1 + arg));
+    } else {
+      res = sum * dpois_wrap(g, x);
     }
   } else if (alph - 1 < x && alph < 0.8 * (x + 50)) {
     double d = dpois_wrap(g, x), sum;
