@@ -205,6 +205,35 @@ def test_baseline_size_batch_properties(built_lib):
     assert len(hard) >= 300 and relerr(one[sub], _oracle(spec).loglike(th[sub], nthreads=8)) <= TOL
 
 
+def test_subnormal_gamma_cdf_follows_the_reference_rounding(built_lib):
+    """R's pgamma_raw redoes results below DBL_MIN / DBL_EPSILON in log space (one exp, one rounding).  Where the value is
+    subnormal with fewer than ~1e9 quanta that single rounding decides every bit, so device and oracle must agree EXACTLY;
+    above that the two differ by their ordinary 1e-13 relative rounding."""
+    from scipy.special import gammaln
+    from covidcurve_b200 import _lib
+    from oracle.oracle import lib
+    Lo = lib()
+    rng = np.random.default_rng(0)
+    n = 12000
+    a = rng.uniform(1800, 2300, n)
+    u = rng.uniform(-744.4, -700.0, n)                       # log P: the subnormal range and a little above
+    f = lambda xx: a * np.log(xx) - xx - gammaln(a + 1) - np.log1p(-xx / (a + 1)) - u
+    lo_, hi_ = np.full(n, 1.0), a - 1.0
+    for _ in range(70):
+        mid = 0.5 * (lo_ + hi_)
+        neg = f(mid) < 0
+        lo_, hi_ = np.where(neg, mid, lo_), np.where(neg, hi_, mid)
+    x = 0.5 * (lo_ + hi_)
+    want = np.array([Lo.cco_pgamma(xi, ai, 1.0, 1, 0) for xi, ai in zip(x, a)])
+    got = _lib.nmath("pgamma", x, a, 1.0)
+    quanta = want / 4.9406564584124654e-324
+    few = (want > 0) & (quanta < 1e9)
+    assert few.sum() > 3000 and np.array_equal(got[few], want[few])
+    rest = (want > 0) & ~few
+    assert np.all(np.abs(got[rest] - want[rest]) <= np.maximum(2 * 4.9406564584124654e-324, 5e-12 * want[rest]))
+    assert np.array_equal(got == 0, want == 0)
+
+
 def test_curves_match_oracle_intermediates(built_lib, modfit):
     spec, g = modfit
     m, o = _model(spec), _oracle(spec)
