@@ -5,6 +5,11 @@
  * reference: src/natcubicspline_loglike_binomial.cpp:79 (pgamma), :216 (dpois), :248,:337 (dbinom),
  * :269 (pweibull); src/natcubicspline_loglike_logit.cpp:337 (dnorm); R/Agecpp2strings.R:73-148
  * (dunif, dnorm, dbeta in the generated prior).
+ *
+ * PARITY UNPINNED in one corner: pnorm_std() below is 0.5 erfc(.) (and its log), not R's pnorm_both() (Cody 1969 rational
+ * approximations; the coefficient tables are not in the reference tree).  In the main range the two agree to ~1e-16; they
+ * differ where pgamma_raw redoes a value below 1.002e-292 that came out of ppois_asymp() in log space (gamma shapes above
+ * ~33 500, i.e. sod < 0.0055): R then uses pnorm's log-tail expansion, this port log(0.5 erfc(.)) of a subnormal.
  */
 #include "nmath_port.h"
 
