@@ -153,6 +153,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    if world > 1:
+        # one process per GPU: keep this rank (and the pinned buffers it first-touches) on the CPUs next to its GPU, so that the
+        # ranks' host->device copies do not cross sockets or share one memory controller
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = "cpus %d..%d" % (min(os.sched_getaffinity(0)), max(os.sched_getaffinity(0)))
+        except Exception as e:  # affinity is an optimisation, never a requirement
+            numa = "unset (%s)" % type(e).__name__
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -340,7 +351,7 @@ def main():
                        "vectors_per_gpu_per_step": V, "layout": "SoA theta[d][V]", "l2": "inputs larger than L2 (%.0f MB per step)" % (d * V * 8 / 1e6),
                        "full_eval_fraction": full_frac},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": d * V * 8, "d2h_bytes_per_step": V * 8, "steps": e2e_steps,
-                    "h2d_gbs_measured": h2d_gbs, "h2d_bound": h2d_gbs * 1e9 / (d * 8) * world},
+                    "h2d_gbs_measured": h2d_gbs, "h2d_bound": h2d_gbs * 1e9 / (d * 8) * world, "cpu_affinity": numa},
             "gpu_launches": args.steps * 5,  # phase-1 pass, bucket offsets, scatter, phase-2 pass, phase-3 pass per step
             "posterior_like": {"value": value_post, "unit": UNIT, "frac_of_fp64_peak": value_post * falg / 1e12 / peak_tf,
                                "vectors": "truth x (1 + 0.02 N(0,1)), clipped to the box"},

@@ -62,9 +62,10 @@ struct cc_model {
   ccdev::KModel k{};
   std::vector<void*> dev_allocs;   // everything cudaMalloc'ed for the tables
   cudaStream_t stream = nullptr;   // library-owned stream
-  cudaStream_t stream2 = nullptr;  // second stream of the double-buffered host path
+  cudaStream_t stream2 = nullptr;  // second and third stream of the triple-buffered host path
+  cudaStream_t stream3 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
   double last_ms = 0.0;
   int last_launches = 0;
   // host staging (pinned) + device staging for CC_MEM_HOST calls
@@ -75,9 +76,9 @@ struct cc_model {
   int sm_count = 0;
   int grid_p2 = 1;                 // resident CTAs of pass C of the batched likelihood
   int grid_max = 1;                // resident CTAs of the evaluation kernel on this device
-  // work buffers of the batched likelihood, one set per launch slot ([0] device-pointer calls, [1],[2] the two host-path
+  // work buffers of the batched likelihood, one set per launch slot ([0] device-pointer calls, [1]..[3] the three host-path
   // streams): records rec[F][cap], regime keys, permutation, histogram + cursors; grown on demand
   struct Work { double* rec = nullptr; int* key = nullptr; int* perm = nullptr; unsigned int* counts = nullptr; long long cap = 0; };
-  Work work[3];
+  Work work[4];
   int nt = 0;                      // 64-day output tiles per evaluation (template parameter of the warp kernels)
 };

@@ -960,9 +960,10 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   }
   cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
-  for (int q = 0; q < 2 && e == cudaSuccess; q++) e = cudaEventCreateWithFlags(&m->ev_stage[q], cudaEventDisableTiming);
+  for (int q = 0; q < 3 && e == cudaSuccess; q++) e = cudaEventCreateWithFlags(&m->ev_stage[q], cudaEventDisableTiming);
   // opt in to large dynamic shared memory once
   m->nt = pick_nt(T);
   if (e == cudaSuccess && m->nt < 0) {
@@ -1020,7 +1021,7 @@ extern "C" void cc_model_destroy(cc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   for (void* p : m->dev_allocs) cudaFree(p);
-  for (int q = 0; q < 3; q++) {
+  for (int q = 0; q < 4; q++) {
     if (m->work[q].rec) cudaFree(m->work[q].rec);
     if (m->work[q].key) cudaFree(m->work[q].key);
     if (m->work[q].perm) cudaFree(m->work[q].perm);
@@ -1029,12 +1030,13 @@ extern "C" void cc_model_destroy(cc_model* m) {
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->d_out) cudaFree(m->d_out);
   if (m->h_pin) cudaFreeHost(m->h_pin);
-  for (int q = 0; q < 2; q++)
+  for (int q = 0; q < 3; q++)
     if (m->ev_stage[q]) cudaEventDestroy(m->ev_stage[q]);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->stream) cudaStreamDestroy(m->stream);
   if (m->stream2) cudaStreamDestroy(m->stream2);
+  if (m->stream3) cudaStreamDestroy(m->stream3);
   delete m;
 }
 
@@ -1117,27 +1119,30 @@ static int ensure_stage(cc_model* m, size_t theta_bytes, size_t out_bytes) {
 typedef int (*launch_fn)(cc_model*, const double*, long long, long long, double*, cudaStream_t, int);
 
 // Host-buffer path: column chunks are copied H2D (2-D copy: d rows of `chunk` doubles), evaluated and copied back,
-// double-buffered over two streams so that copies overlap the kernel.  Pinned caller memory gives true overlap;
+// triple-buffered over three streams so that the copy engine never waits for a staging slot: while chunk k computes,
+// chunk k+1 is uploaded and chunk k+2 can already start uploading (with two slots the upload of k+2 had to wait for the
+// kernels of k, which cost 25 % when four ranks share the host's PCIe bandwidth).  Pinned caller memory gives true overlap;
 // pageable memory still works (the driver stages it).
 static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long long n, long long ld, double* out) {
   const int d = m->k.d;
+  constexpr int kSlots = 3;
   // Chunk sizes grow geometrically (64k, 128k, ... up to 512k vectors): only the first chunk's upload and the last
   // chunk's download are exposed, so they are kept small, while the bulk runs in large launches (measured on B200 at
   // 2^20 vectors: fixed 128k chunks 56.8 M evals/s, 256k 58.6, 512k 60.1; profiles/r1_summary.md)
   long long cmax = 1 << 19;
   if (const char* e = std::getenv("CC_HOST_CHUNK")) cmax = std::max<long long>(1024, (std::atoll(e) + 1023) & ~1023LL);  // developer tuning
   cmax = std::min<long long>(cmax, (n + 1023) & ~1023LL);
-  int rc = ensure_stage(m, (size_t)2 * d * cmax * sizeof(double), (size_t)2 * cmax * sizeof(double));
+  int rc = ensure_stage(m, (size_t)kSlots * d * cmax * sizeof(double), (size_t)kSlots * cmax * sizeof(double));
   if (rc) return rc;
-  if (fn == launch_loglike)  // size both work slots for the largest chunk now: growing them mid-pipeline would synchronise the device
-    for (int slot = 1; slot <= 2; slot++)
+  if (fn == launch_loglike)  // size the work slots for the largest chunk now: growing them mid-pipeline would synchronise the device
+    for (int slot = 1; slot <= kSlots; slot++)
       if ((rc = ensure_work(m, slot, std::min(cmax, n)))) return rc;
-  cudaStream_t st[2] = {m->stream, m->stream2};
+  cudaStream_t st[kSlots] = {m->stream, m->stream2, m->stream3};
   CC_CUDA(cudaEventRecord(m->ev0, st[0]));
   m->last_launches = 0;
   int q = 0;
   long long chunk = std::min<long long>(cmax, 1 << 16);
-  for (long long c0 = 0; c0 < n; q ^= 1) {
+  for (long long c0 = 0; c0 < n; q = (q + 1) % kSlots) {
     long long cn = std::min(chunk, n - c0);
     if (n - c0 - cn < (1 << 15)) cn = std::min(n - c0, cmax);  // do not leave a sliver behind
     double* dth = m->d_stage + (size_t)q * d * cmax;
@@ -1151,8 +1156,10 @@ static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long l
     c0 += cn;
     chunk = std::min<long long>(2 * chunk, cmax);
   }
-  CC_CUDA(cudaEventRecord(m->ev_stage[1], st[1]));
-  CC_CUDA(cudaStreamWaitEvent(st[0], m->ev_stage[1], 0));
+  for (int j = 1; j < kSlots; j++) {
+    CC_CUDA(cudaEventRecord(m->ev_stage[j], st[j]));
+    CC_CUDA(cudaStreamWaitEvent(st[0], m->ev_stage[j], 0));
+  }
   CC_CUDA(cudaEventRecord(m->ev1, st[0]));
   CC_CUDA(cudaStreamSynchronize(st[0]));
   float ms = 0.f;
