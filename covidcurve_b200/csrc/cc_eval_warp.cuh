@@ -52,24 +52,26 @@ __device__ __forceinline__ void toeplitz_dmma(const double* __restrict__ xs, con
   double acc1[NT][2];
 #pragma unroll
   for (int P = 0; P < NT; P++) acc[P][0] = acc[P][1] = acc1[P][0] = acc1[P][1] = 0.0;
-#pragma unroll
-  for (int D = 0; D < NT; D++) {
+  // lag dl = 8 D + e needs series block row P - D at offset e: with e outermost the NT B-fragment pairs are loaded once
+  // per e and shared by all D (half the shared-memory loads of the D-outer order)
 #pragma unroll 2
-    for (int e = 0; e < 8; e++) {
+  for (int e = 0; e < 8; e++) {
+    const double* b = bp - 12 * e;
+    double b0[NT], b1[NT];
+#pragma unroll
+    for (int q = 0; q < NT; q++) {
+      b0[q] = b[96 * q];
+      b1[q] = b[96 * q + 4];
+    }
+#pragma unroll
+    for (int D = 0; D < NT; D++) {
       const int dl = 8 * D + e;
       if (dl >= nb) break;
       const double a0 = ap[8 * dl], a1 = ap[8 * dl - 4];
-      const double* b = bp - 12 * dl;
-      double b0[NT], b1[NT];
 #pragma unroll
       for (int P = D; P < NT; P++) {
-        b0[P] = b[96 * P];
-        b1[P] = b[96 * P + 4];
-      }
-#pragma unroll
-      for (int P = D; P < NT; P++) {
-        dmma884(acc[P][0], acc[P][1], a0, b0[P]);
-        dmma884(acc1[P][0], acc1[P][1], a1, b1[P]);
+        dmma884(acc[P][0], acc[P][1], a0, b0[P - D]);
+        dmma884(acc1[P][0], acc1[P][1], a1, b1[P - D]);
       }
     }
   }
