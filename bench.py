@@ -342,9 +342,9 @@ def main():
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-            # (profiles/r1_phase2_box_metrics.txt: 170.3 MB read + 12.9 MB written for 262 144 box-uniform evaluations = 699 B per
+            # (profiles/r1_phase2_box_metrics.txt: 170.3 MB read + 13.5 MB written for 262 144 box-uniform evaluations = 701 B per
             # evaluation: the SoA record handed over by the thread-per-vector pass, its result fields, the permutation)
-            "traffic": 699.0 * V, "traffic_source": "ncu --set full capture of loglike_phase2_kernel at 262 144 vectors, per-evaluation bytes x vectors of this launch",
+            "traffic": 701.0 * V, "traffic_source": "ncu --set full capture of loglike_phase2_kernel at 262 144 vectors, per-evaluation bytes x vectors of this launch",
             "algorithmic_bytes": float(alg_bytes),
             "kernel": "loglike_phase2_kernel (the per-day pass; kernel_ms covers the whole 5-launch pipeline of one cc_loglike_batch call)", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
             "peak_source": "max of cc_fp64_peak_probe (register-resident DFMA chains: %.2f) and cc_dmma_probe (mma.sync m8n8k4 f64: %.2f), measured "
