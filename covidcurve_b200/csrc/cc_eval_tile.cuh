@@ -746,6 +746,36 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
 
 // ------------------------------------------------------------------------------------------------ phase 3
 // G = 32 / E lanes cooperate on one vector: lane = sub * E + e; terms are strided over sub and xor-reduced over the high bits
+// one term of the chained binomial on the age split (binomial.cpp:227-251): stratum a, running subtraction in the reference's order
+template <typename Get>
+__device__ __forceinline__ double p3_l2_term(const KModel& m, const RecLayout& L, Get get, int a, double texpd, double sum_unc) {
+  double te = texpd;
+  for (int b = 0; b < a; b++) te -= get(L.nm + b) * sum_unc;
+  return dbinom_log_shared(round(get(L.nm + a) * sum_unc), round(te), m.l2_prob[a]);
+}
+
+// one term of the serology likelihood (binomial.cpp:316-340; logit.cpp:314-339): survey-stratum cell k = s * A + a
+template <typename Get>
+__device__ __forceinline__ double p3_l3_term(const KModel& m, const RecLayout& L, Get get, int k, double sens, double spec) {
+  const int A = m.A, s = k / A, a = k - s * A;
+  const double frac = (get(L.ne + a) * get(L.o_base + s)) / (double)m.demog[a];
+  const double prev = sens * frac + (1 - spec) * (1 - frac);
+  if (m.binomial) {
+    const int kind = m.l3_kind[k];
+    if (kind == 1) {
+      const double x = m.sero_a[k], nn = m.sero_b[k];
+      if (!(prev >= 0.0 && prev <= 1.0)) return d_nan();
+      if (x == 0.0) return (nn == 0.0) ? 0.0 : nn * log(1 - prev);
+      if (x == nn) return nn * log(prev);
+      return m.l3_lchoose[k] + x * log(prev) + (nn - x) * log(1 - prev);
+    }
+    return (kind == 2) ? dbinom_log_shared(m.sero_a[k], m.sero_b[k], prev) : 0.0;
+  }
+  const double eps = DBL_MIN / 100.0;
+  const double lg = log((prev + eps) / (1 - (prev + eps)));
+  return dnorm_log(lg, m.sero_a[k], m.sero_b[k]);
+}
+
 __device__ inline double tile_phase3(const KModel& m, const RecLayout& L, const double* __restrict__ scr, int e, int sub, int G, int E,
                                    long long stride = 32) {
   const int A = m.A, S = m.S;
@@ -754,43 +784,38 @@ __device__ inline double tile_phase3(const KModel& m, const RecLayout& L, const 
   double tail = 0.0;
   if (pass) {
     const double texpd = get(L.o_texpd), sum_unc = get(L.o_sunc);
-    // S9: chained binomial on the age split (binomial.cpp:227-251), running subtraction in the reference's order
-    for (int a = sub; a < A - 1; a += G) {
-      double te = texpd;
-      for (int b = 0; b < a; b++) te -= get(L.nm + b) * sum_unc;
-      tail += dbinom_log_shared(round(get(L.nm + a) * sum_unc), round(te), m.l2_prob[a]);
-    }
-    // S13: serology
+    for (int a = sub; a < A - 1; a += G) tail += p3_l2_term(m, L, get, a, texpd, sum_unc);   // S9
     const double sens = get(L.sens), spec = get(L.spec);
-    for (int k = sub; k < S * A; k += G) {
-      const int s = k / A, a = k - s * A;
-      const double frac = (get(L.ne + a) * get(L.o_base + s)) / (double)m.demog[a];
-      const double prev = sens * frac + (1 - spec) * (1 - frac);
-      if (m.binomial) {
-        const int kind = m.l3_kind[k];
-        if (kind == 1) {
-          const double x = m.sero_a[k], nn = m.sero_b[k];
-          double v;
-          if (!(prev >= 0.0 && prev <= 1.0)) v = d_nan();
-          else if (x == 0.0) v = (nn == 0.0) ? 0.0 : nn * log(1 - prev);
-          else if (x == nn) v = nn * log(prev);
-          else v = m.l3_lchoose[k] + x * log(prev) + (nn - x) * log(1 - prev);
-          tail += v;
-        } else if (kind == 2) {
-          tail += dbinom_log_shared(m.sero_a[k], m.sero_b[k], prev);
-        }
-      } else {
-        const double eps = DBL_MIN / 100.0;
-        const double lg = log((prev + eps) / (1 - (prev + eps)));
-        tail += dnorm_log(lg, m.sero_a[k], m.sero_b[k]);
-      }
-    }
+    for (int k = sub; k < S * A; k += G) tail += p3_l3_term(m, L, get, k, sens, spec);        // S13
   }
   for (int o = E; o < 32; o <<= 1) tail += __shfl_xor_sync(0xffffffffu, tail, o);
   if (!pass) return -CC_OVERFLO;
   double loglik = get(L.o_l1) + tail;
   if (!isfinite(loglik)) loglik = -CC_OVERFLO;
   return loglik;
+}
+
+// The same for the Metropolis sweep (one warp, record in shared memory), with the two sums kept apart: a single-site proposal
+// that cannot change the age split (test characteristics, seroconversion) or the serology term (IFRs, onset-to-death delay)
+// reuses the cached sum.  Returns false when the evaluation has failed a validity check.
+__device__ inline bool sweep_phase3(const KModel& m, const RecLayout& L, const double* rec, bool do_l2, bool do_l3, double& l2, double& l3) {
+  const int lane = threadIdx.x & 31, A = m.A, S = m.S;
+  auto get = [&](int f) { return rec[f]; };
+  const bool pass = get(L.flags) != 0.0 && get(L.o_status) == 0.0;
+  if (!pass) return false;
+  if (do_l2) {
+    const double texpd = get(L.o_texpd), sum_unc = get(L.o_sunc);
+    double v = 0.0;
+    for (int a = lane; a < A - 1; a += 32) v += p3_l2_term(m, L, get, a, texpd, sum_unc);
+    l2 = warp_sum(v);
+  }
+  if (do_l3) {
+    const double sens = get(L.sens), spec = get(L.spec);
+    double v = 0.0;
+    for (int k = lane; k < S * A; k += 32) v += p3_l3_term(m, L, get, k, sens, spec);
+    l3 = warp_sum(v);
+  }
+  return true;
 }
 
 // one term of the generated logprior

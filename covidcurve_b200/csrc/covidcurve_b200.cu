@@ -311,7 +311,7 @@ struct SweepSmem {
   double *q_thp, *q_php, *q_adj, *q_ptn, *q_logu;  // the sweep's d proposals, drawn up front (q_logu[i] becomes the accept flag)
 };
 struct SweepCacheLayout {
-  int rec, xs, gs, auc, sk, scal, size;  // offsets (doubles) into a particle's cache block; scal: tot, s1, sa_obs, s_all_auc, s_unc, irregular, valid
+  int rec, xs, gs, auc, sk, scal, size;  // offsets (doubles) into a particle's cache block; scal: tot, s1, sa_obs, s_all_auc, s_unc, irregular, valid, l2, l3
   int nxs, ngs, nauc, nsk, nrec;
 };
 __host__ __device__ inline SweepCacheLayout sweep_cache_layout(int K, int A, int S, int NT) {
@@ -319,7 +319,7 @@ __host__ __device__ inline SweepCacheLayout sweep_cache_layout(int K, int A, int
   SweepCacheLayout c;
   c.nrec = (L.F + 3) & ~3; c.nxs = 12 * (8 * NT + 7); c.ngs = 64 * NT + 16; c.nauc = 64 * NT; c.nsk = 64 * NT + 4;
   c.rec = 0; c.xs = c.rec + c.nrec; c.gs = c.xs + c.nxs; c.auc = c.gs + c.ngs; c.sk = c.auc + c.nauc; c.scal = c.sk + c.nsk;
-  c.size = c.scal + 8;
+  c.size = c.scal + 12;
   return c;
 }
 __host__ __device__ inline size_t sweep_smem_doubles(int d, int K, int A, int S, int NT) {
@@ -341,7 +341,9 @@ __device__ inline SweepSmem carve_sweep(double* q, int d, const SweepCacheLayout
   return w;
 }
 
-enum : int { kDepWeights = 1, kDepSpline = 2, kDepGamma = 4, kDepSero = 8 };
+enum : int { kDepWeights = 1, kDepSpline = 2, kDepGamma = 4, kDepSero = 8,
+             kKeepL3 = 16,   // the proposal cannot change the serology term (an IFR, the onset-to-death delay)
+             kKeepL2 = 32 }; // the proposal cannot change the age split (test sensitivity / specificity, seroconversion, seroreversion)
 
 template <typename T>
 __device__ __forceinline__ void swap_ptr(T*& a, T*& b) { T* t = a; a = b; b = t; }
@@ -456,6 +458,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
     __syncwarp();
     double tot_cur = 0.0;
     L1Sums sums_cur = {0.0, 0.0, 0.0, 0.0, 1};
+    double l2_cur = 0.0, l3_cur = 0.0;  // age-split and serology sums of the current state
     bool unbuilt = cache[CL.scal + 6] == 0.0;
     if (!unbuilt) {
       // caches of the current state, left by the previous sweep
@@ -463,6 +466,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
       tot_cur = cache[CL.scal + 0];
       sums_cur.s1 = cache[CL.scal + 1]; sums_cur.sa_obs = cache[CL.scal + 2]; sums_cur.s_all_auc = cache[CL.scal + 3];
       sums_cur.s_unc = cache[CL.scal + 4]; sums_cur.irregular = (int)cache[CL.scal + 5];
+      l2_cur = cache[CL.scal + 7]; l3_cur = cache[CL.scal + 8];
     } else {
       // First sweep of a particle: nothing is cached yet.  An all-zero record reads as "no usable caches" (flags == 0), so
       // every proposal is evaluated from scratch until the first one is accepted and becomes the cached state.
@@ -537,7 +541,11 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
         }
       }
       __syncwarp();
-      const double llp = tile_phase3(m, L, w.recB, 0, lane, 32, 1, 1);
+      // age split and serology term: recomputed only if the proposed parameter can change them
+      double l2_p = l2_cur, l3_p = l3_cur;
+      const bool p3ok = sweep_phase3(m, L, w.recB, from_invalid || !(dep & kKeepL2), from_invalid || !(dep & kKeepL3), l2_p, l3_p);
+      double llp = p3ok ? w.recB[L.o_l1] + (l2_p + l3_p) : -CC_OVERFLO;
+      if (!isfinite(llp)) llp = -CC_OVERFLO;
       // prior: only term i (and a Jacobian term if i is a reference parameter) changes
       double pt_new = 0.0, jac_new[3] = {0.0, 0.0, 0.0};
       {
@@ -567,7 +575,10 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
           unbuilt = false;
           tot_cur = tot_p;
           sums_cur = sums_p;
+          l2_cur = l2_p;
+          l3_cur = l3_p;
           if (lane == 0) {
+            cache[CL.scal + 7] = l2_cur; cache[CL.scal + 8] = l3_cur;
             cache[CL.scal + 0] = tot_cur;
             cache[CL.scal + 1] = sums_cur.s1; cache[CL.scal + 2] = sums_cur.sa_obs; cache[CL.scal + 3] = sums_cur.s_all_auc;
             cache[CL.scal + 4] = sums_cur.s_unc; cache[CL.scal + 5] = (double)sums_cur.irregular;
@@ -917,22 +928,27 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   {
     auto mark = [&](int row, int bit) { if (row >= 0 && row < d) dep[row] |= bit; };
     for (int a = 0; a < A; a++) {
-      mark(de->idx_ifr[a], kDepWeights);
+      mark(de->idx_ifr[a], kDepWeights | kKeepL3);
       if (A > 1) mark(de->idx_noise[a], kDepWeights);
     }
-    mark(de->idx_sens, kDepWeights);
-    mark(de->idx_spec, kDepWeights);
-    if (de->reparam_ifr) mark(de->idx_max_ma, kDepWeights);
+    mark(de->idx_sens, kDepWeights | kKeepL2);
+    mark(de->idx_spec, kDepWeights | kKeepL2);
+    if (de->reparam_ifr) mark(de->idx_max_ma, kDepWeights | kKeepL3);
     for (int i = 0; i < K - 1; i++) mark(de->idx_knots[i], kDepSpline);
     for (int i = 0; i < K; i++) mark(de->idx_infxn[i], kDepSpline);
     if (de->reparam_knots) mark(de->idx_rel_knot, kDepSpline);
     if (de->reparam_infxn) mark(de->idx_rel_infxn, kDepSpline);
-    mark(de->idx_mod, kDepGamma);
-    mark(de->idx_sod, kDepGamma);
-    mark(de->idx_sero_con_rate, kDepSero);
+    mark(de->idx_mod, kDepGamma | kKeepL3);
+    mark(de->idx_sod, kDepGamma | kKeepL3);
+    mark(de->idx_sero_con_rate, kDepSero | kKeepL2);
     if (de->account_serorev) {
-      mark(de->idx_sero_rev_shape, kDepSero);
-      mark(de->idx_sero_rev_scale, kDepSero);
+      mark(de->idx_sero_rev_shape, kDepSero | kKeepL2);
+      mark(de->idx_sero_rev_scale, kDepSero | kKeepL2);
+    }
+    // a row that plays two roles (not possible through the R interface, but the descriptor allows it) keeps nothing
+    for (int i = 0; i < d; i++) {
+      const int roles = ((dep[i] & kDepWeights) ? 1 : 0) + ((dep[i] & kDepSpline) ? 1 : 0) + ((dep[i] & kDepGamma) ? 1 : 0) + ((dep[i] & kDepSero) ? 1 : 0);
+      if (roles != 1 || ((dep[i] & kKeepL2) && (dep[i] & kKeepL3))) dep[i] &= ~(kKeepL2 | kKeepL3);
     }
   }
   std::vector<double> sa(de->sero_a, de->sero_a + (size_t)S * A), sb(de->sero_b, de->sero_b + (size_t)S * A);
