@@ -9,6 +9,7 @@ Shapes (A strata, K knots, T days, S surveys, M last survey day):
   cfg2: A=5,  T=200, S=2, logit-normal serology, seroreversion, 4 chains x 20 rungs
   cfg3: A=10, T=300, S=3, binomial serology, 64 chains x 50 rungs           (also cfg5: 1M random vectors)
   cfg4: A=17, T=400, S=3, binomial serology, 4096 chains x 64 rungs
+  long: A=4,  T=500, K=6, S=3, binomial serology, seroreversion (test shape for the T > 448 kernels; not a BASELINE config)
 """
 from __future__ import annotations
 
@@ -24,6 +25,8 @@ CONFIGS = {
     "cfg4": dict(A=17, T=400, K=5, surveys=((150, 160), (250, 260), (370, 380)), binomial=True, serorev=False, chains=4096, rungs=64),
 }
 CONFIGS["cfg5"] = dict(CONFIGS["cfg3"], chains=0, rungs=0)
+# not a BASELINE config: a long series (T > 448 -> the 16-tile kernels) with six knots and seroreversion, for the parity tests
+CONFIGS["long"] = dict(A=4, T=500, K=6, surveys=((200, 210), (330, 340), (470, 480)), binomial=True, serorev=True, chains=2, rungs=3)
 
 
 def _natural_spline(x, y):

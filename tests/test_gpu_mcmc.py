@@ -14,7 +14,8 @@ def _run_both(spec, **kw):
     mc.advance(kw["burnin"] + kw["samples"] - 1)
     got, diag = mc.fetch(), mc.diagnostics()
     o_kw = {k: v for k, v in kw.items() if k not in ("chain_offset",)}
-    want = Oracle(spec).mcmc(nthreads=4, chain_offset=kw.get("chain_offset", 0), **o_kw)
+    o_kw.setdefault("nthreads", 4)
+    want = Oracle(spec).mcmc(chain_offset=kw.get("chain_offset", 0), **o_kw)
     return got, diag, want, mc
 
 
@@ -44,6 +45,82 @@ def test_trajectory_parity_logit_serorev_reparam(built_lib):
     got, diag, want, _ = _run_both(spec, burnin=25, samples=15, rungs=3, chains=2, seed=9)
     np.testing.assert_allclose(got["theta"], want["theta"], rtol=1e-9)
     np.testing.assert_allclose(got["loglike"], want["loglike"], rtol=1e-9)
+
+
+def _assert_same_trajectory(got, diag, want):
+    np.testing.assert_allclose(got["theta"], want["theta"], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(got["loglike"], want["loglike"], rtol=1e-9)
+    np.testing.assert_allclose(got["logprior"], want["logprior"], rtol=1e-9)
+    # identical accept / reject decisions: a state either moved in both runs or in neither
+    assert np.array_equal(np.diff(got["theta"], axis=2) != 0, np.diff(want["theta"], axis=2) != 0)
+    if want["beta"].size > 1:
+        np.testing.assert_allclose(diag["mc_accept"], want["mc_accept"], rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("serorev", [False, True])
+@pytest.mark.parametrize("from_truth", [False, True])
+def test_trajectory_parity_cfg3_shape(built_lib, serorev, from_truth):
+    """BASELINE configs[2] - the shape bench.py's MCMC leg times (A = 10, T = 300: the 5-tile kernels; 9 strata in the
+    chained binomial of binomial.cpp:227-251), with and without seroreversion.  The hot rung (beta = 0) walks the prior and
+    so in and out of failed population checks: the cached sweep must rebuild from an invalid state."""
+    from covidcurve_b200 import synth
+    spec, truth = synth.make_spec("cfg3", serorev=serorev)
+    kw = dict(burnin=18, samples=12, rungs=4, chains=2, seed=31 + serorev, GTI_pow=2.0)
+    if from_truth:
+        kw["init"] = np.tile(synth.true_theta(spec, truth), (2, 1))
+    got, diag, want, mc = _run_both(spec, **kw)
+    assert got["theta"].shape == (2, 4, 30, spec.d)
+    _assert_same_trajectory(got, diag, want)
+
+
+def test_trajectory_parity_cfg4_shape(built_lib):
+    """BASELINE configs[3]: 17 strata x 400 days (the 7-tile kernels, d = 48)."""
+    from covidcurve_b200 import synth
+    spec, truth = synth.make_spec("cfg4")
+    init = np.stack([synth.true_theta(spec, truth), spec.pinit])
+    got, diag, want, _ = _run_both(spec, burnin=14, samples=10, rungs=3, chains=2, seed=44, GTI_pow=3.0, init=init)
+    _assert_same_trajectory(got, diag, want)
+
+
+def test_trajectory_parity_cfg4_serorev_logit(built_lib):
+    from covidcurve_b200 import synth
+    spec, truth = synth.make_spec("cfg4", serorev=True, binomial=False)
+    assert spec.d == 50
+    got, diag, want, _ = _run_both(spec, burnin=10, samples=6, rungs=2, chains=2, seed=45,
+                                   init=np.tile(synth.true_theta(spec, truth), (2, 1)))
+    _assert_same_trajectory(got, diag, want)
+
+
+def test_trajectory_parity_long_series(built_lib):
+    """T = 500 > 448 days: the 16-tile kernels, six knots (interval thresholds beyond the three kept in registers),
+    seroreversion over M = 480 days."""
+    from covidcurve_b200 import synth
+    spec, truth = synth.make_spec("long")
+    assert spec.T == 500 and spec.K == 6
+    init = np.stack([synth.true_theta(spec, truth), spec.pinit])
+    got, diag, want, _ = _run_both(spec, burnin=14, samples=10, rungs=3, chains=2, seed=46, GTI_pow=2.0, init=init)
+    _assert_same_trajectory(got, diag, want)
+
+
+def test_trajectory_parity_through_disordered_knots(built_lib):
+    """Overlapping boxes for the two middle knots: the hot rung (beta = 0) accepts disordered knots (binomial.cpp:88-96) and
+    failed population checks (:170-184) and comes back several times, so the sweep leaves and re-enters the state without any
+    cached per-day arrays (need_all / from_invalid rebuilds)."""
+    from covidcurve_b200 import synth
+    spec, truth = synth.make_spec("cfg3")
+    k = [spec.index(n) for n in spec.Knotparams]
+    lo, hi = spec.pmin[k[1]], spec.pmax[k[2]]
+    for i in (k[1], k[2]):
+        spec.pmin[i] = spec.dsc1[i] = lo
+        spec.pmax[i] = spec.dsc2[i] = hi
+    init = np.tile(synth.true_theta(spec, truth), (2, 1))
+    got, diag, want, _ = _run_both(spec, burnin=40, samples=20, rungs=3, chains=2, seed=47, init=init)
+    x = want["theta"][:, 0][:, :, k]
+    dis = ~np.all(np.diff(x, axis=2) > 0, axis=2)
+    inv = want["loglike"][:, 0, :] == -(np.finfo(float).max / 100)
+    assert (dis[:, :-1] & ~dis[:, 1:]).sum() >= 4 and (~dis[:, :-1] & dis[:, 1:]).sum() >= 4, "knot order should be lost and regained"
+    assert (inv[:, :-1] & ~inv[:, 1:]).sum() >= 8
+    _assert_same_trajectory(got, diag, want)
 
 
 def test_sharding_is_invisible(built_lib, modfit):
