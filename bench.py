@@ -1,21 +1,30 @@
 #!/usr/bin/env python
 """bench.py - throughput of the COVIDCurve hot path on B200 (and of the CPU reference arm).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--vectors V] [--mcmc-iters I]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--vectors V]
 
-Workload (BASELINE.json configs[4] = "cfg5", the likelihood-only microbenchmark on the configs[2] shape the metric
-is quoted on): V (default 2^20) random parameter vectors per GPU of the 10-age-band / 300-day / 5-knot / 3-serosurvey
-binomial model (d = 34), synthetic data (covidcurve_b200/synth.py, seeds 20201/20202).  One "step" = one pass of
-the batched log-likelihood over all V vectors.  `value` = log-likelihood evaluations per second, whole job
-(all ranks), inputs resident in HBM.  `e2e` = the same through the C ABI with HOST (pinned) buffers: host->device
-copy of the parameter vectors and device->host copy of the log-likelihoods inside the timed region.
-`mcmc` = GPU-resident Metropolis-coupled MCMC on configs[2] (64 chains x 50 rungs per GPU): iterations/s summed over
-all chains x rungs (one iteration = one sweep of d single-site updates + the coupling pass).
+Likelihood leg (BASELINE.json configs[4] = "cfg5", the likelihood-only microbenchmark on the configs[2] shape the metric is
+quoted on): V = 2^20 random parameter vectors of the 10-age-band / 300-day / 5-knot / 3-serosurvey binomial model (d = 34),
+synthetic data (covidcurve_b200/synth.py, seeds 20201/20202).  One "step" = one pass of the batched log-likelihood over all V
+vectors, SPLIT EVENLY over the N ranks (strong scaling, V / N vectors per GPU; no collective).
+  value  = log-likelihood evaluations per second, whole job, inputs resident in HBM;
+  weak   = the same with V vectors on EVERY GPU (second figure, N > 1 only);
+  e2e    = `value`'s workload through the C ABI with HOST (pinned) buffers: host->device copy of the parameter vectors and
+           device->host copy of the log-likelihoods inside the timed region; `e2e.pageable` = the same from plain malloc'ed
+           memory (what an R caller's REAL(theta) is).
+MCMC legs (GPU-resident Metropolis-coupled MCMC; one iteration = one sweep of d single-site updates + the coupling pass;
+figures are iterations/s summed over all chains x rungs; device time from CUDA events on the library's stream):
+  mcmc       = BASELINE configs[3] "cfg4": 17 age bands x 400 days, 4096 chains x 64 rungs SHARDED over the N GPUs
+               (4096 / N chains per GPU, RNG keyed by global chain id), followed by the run's only collective:
+               an NCCL all-gather of the cold-rung sampling draws + the 3 x d all-reduce form of R-hat (`collective`);
+  mcmc_cfg3  = BASELINE configs[2] "cfg3": 64 chains x 50 rungs on one GPU (replicated per GPU when N > 1).
+Both check their final cold-rung states against the CPU oracle.  cpu_baseline / --impl reference time the oracle port of the
+reference (likelihood and the drjacoby-equivalent MCMC loop) on the host cores: 1 thread and all threads.
 
-Multi-GPU: launched by torchrun, one rank per GPU; vectors / chains are sharded with no data-path collective (weak
-scaling: V vectors and 64 x 50 particles per GPU); timing = max over ranks of CUDA-event time between barriers.
+Multi-GPU: launched by torchrun, one rank per GPU; timing = max over ranks of CUDA-event time between barriers.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,12 +41,36 @@ from covidcurve_b200 import synth  # noqa: E402
 
 METRIC = "loglike_evals_per_sec"
 UNIT = "evals/s"
+WORKLOAD = "cfg5: likelihood-only, 10 age bands x 300 days x 5 knots x 3 serosurveys, binomial (d=34)"
 
 
 def f_alg(spec):
     """Algorithmic flops per full evaluation: T(T+1) + serorev*M(M+1) + 3*S*M + 10*T."""
     T, M, S = spec.T, spec.M, spec.S
     return T * (T + 1) + (M * (M + 1) if spec.account_serorev else 0) + 3 * S * M + 10 * T
+
+
+def source_digest():
+    """sha256 over the CUDA sources: ties a committed ncu capture (profiles/r2_traffic.json) to the build it measured."""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "covidcurve_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        h.update(f.encode())
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """dram bytes per evaluation of the dominant kernel from the committed ncu --set full capture, valid only for the build
+    whose sources it was taken on (no constant survives a kernel change silently)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    except Exception:
+        return None, "no profiles/r2_traffic.json"
+    if t.get("source_digest") != source_digest():
+        return None, "profiles/r2_traffic.json was captured on sources %s, this build is %s: not reported" % (t.get("source_digest"), source_digest())
+    return t, "profiles/r2_traffic.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of %s at %d vectors)" % (
+        t.get("kernel"), t.get("vectors", 0))
 
 
 class ClockSampler:
@@ -50,7 +83,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.nv, self.stop_flag = index, [], None, None, False
-        self.sm, self.mx, self.reasons = [], None, set()
+        self.sm, self.mx, self.reasons, self.power = [], None, set(), []
 
     def start(self):
         try:
@@ -61,7 +94,7 @@ class ClockSampler:
             self.nv = pynvml
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-            return
+            return self
         except Exception:
             self.nv = None
         try:
@@ -71,6 +104,7 @@ class ClockSampler:
             self.t.start()
         except OSError:
             self.proc = None
+        return self
 
     def _poll(self):
         nv = self.nv
@@ -79,6 +113,7 @@ class ClockSampler:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
                 self.reasons.update(name for bit, name in self.BITS.items() if mask & bit)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
             time.sleep(0.005)
@@ -91,7 +126,8 @@ class ClockSampler:
         if self.nv is not None:
             self.stop_flag = True
             self.t.join(timeout=1)
-            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": float(np.min(self.sm)) if self.sm else None,
+                    "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "power_w_max": float(np.max(self.power)) if self.power else None,
                     "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -109,19 +145,45 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi"}
 
 
-def cpu_reference_rate(spec, theta, seconds, threads):
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_loglike_rate(o, theta, seconds, threads):
     """evals/s of the CPU oracle (loop-for-loop restatement of the reference, g++ -O2) on `threads` host threads."""
-    from oracle.oracle import Oracle
-    o = Oracle(spec)
-    probe = theta[: 64 * threads]
+    probe = theta[: 32 * threads]
     t0 = time.perf_counter()
     o.loglike(probe, nthreads=threads)
     rate = len(probe) / (time.perf_counter() - t0)
-    n = int(max(threads * 64, min(len(theta), rate * seconds)))
+    n = int(max(threads * 32, min(len(theta), rate * seconds)))
     t0 = time.perf_counter()
-    o.loglike(theta[:n], nthreads=threads)
+    out = o.loglike(theta[:n], nthreads=threads)
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    return n / dt, n, dt, out
+
+
+def cpu_mcmc_rate(cfg, threads, seconds):
+    """chain-rung iterations/s of the oracle's drjacoby-equivalent loop (oracle/cc_oracle_mcmc.cpp) on `threads` host threads:
+    one chain per thread like drjacoby's `cluster=` mode, a reduced ladder (4 rungs) and as many iterations as fit the budget."""
+    from oracle.oracle import Oracle
+    spec, truth = synth.make_spec(cfg)
+    o = Oracle(spec)
+    rungs, chains = 4, threads
+    init = np.tile(synth.true_theta(spec, truth), (chains, 1))
+    t0 = time.perf_counter()
+    o.loglike(init[:1])
+    per_eval = max(time.perf_counter() - t0, 1e-4)
+    iters = int(max(3, min(200, seconds / (per_eval * spec.d * rungs))))
+    t0 = time.perf_counter()
+    o.mcmc(burnin=iters, samples=0, rungs=rungs, chains=chains, seed=synth.SEED_MCMC, init=init, nthreads=threads)
+    dt = time.perf_counter() - t0
+    done = chains * rungs * (iters - 1)          # iteration 1 is the initial state
+    return {"iter_per_sec_all_chains_x_rungs": done / dt, "loglike_evals_per_sec": done * spec.d / dt, "cores": threads,
+            "sample": "%s: %d chains x %d rungs x %d iterations (d=%d), %.1f s" % (cfg, chains, rungs, iters - 1, spec.d, dt)}
 
 
 def run_reference(args, rank, world):
@@ -129,11 +191,11 @@ def run_reference(args, rank, world):
     R + Rcpp + libRmath, absent from this image) with all host threads, on the same config / metric."""
     if rank != 0:
         return
+    from oracle.oracle import Oracle
     spec, _ = synth.make_spec("cfg3")
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     per_step = args.ref_vectors
     theta = synth.random_theta(spec, per_step, seed=synth.SEED_THETA, bad_frac=0.01)
-    from oracle.oracle import Oracle
     o = Oracle(spec)
     for _ in range(args.warmup):
         o.loglike(theta[: max(cores * 16, per_step // 8)], nthreads=cores)
@@ -142,30 +204,40 @@ def run_reference(args, rank, world):
         o.loglike(theta, nthreads=cores)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
+    one, n1, dt1, _ = cpu_loglike_rate(o, theta, 4.0, 1)
     sample = "%d random cfg5 vectors per step (seed %d), %d threads, g++ -O2 oracle port" % (per_step, synth.SEED_THETA, cores)
+    mc = None
+    if not args.no_mcmc:
+        mc = {"cfg3_all_cores": cpu_mcmc_rate("cfg3", cores, 6.0), "cfg3_1_core": cpu_mcmc_rate("cfg3", 1, 5.0),
+              "cfg4_all_cores": cpu_mcmc_rate("cfg4", cores, 8.0)}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg5: likelihood-only, 10 age bands x 300 days x 5 knots x 3 serosurveys, binomial (d=34)",
-                   "vectors_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "vectors_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "value_1_core": one, "sample_1_core": "%d vectors, %.1f s, 1 thread" % (n1, dt1)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mcmc_cpu": mc,
         "gpu_launches": 0,
     }))
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--vectors", type=int, default=1 << 20, help="parameter vectors per GPU per step")
+    ap.add_argument("--vectors", type=int, default=1 << 20, help="parameter vectors per step (whole job; split over the ranks)")
     ap.add_argument("--ref-vectors", type=int, default=8192, help="vectors per step of the CPU reference arm")
-    ap.add_argument("--mcmc-iters", type=int, default=30, help="timed MCMC iterations (0 = skip the MCMC leg)")
-    ap.add_argument("--mcmc-settle", type=int, default=100, help="untimed MCMC iterations before the timed ones")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--mcmc-iters", type=int, default=-1, help="timed iterations of the cfg4 MCMC leg (-1: 25 per GPU, 12..200)")
+    ap.add_argument("--mcmc-settle", type=int, default=40, help="untimed iterations before the timed ones (bandwidth adaptation)")
+    ap.add_argument("--mcmc-chains", type=int, default=0, help="total chains of the cfg4 leg (0: BASELINE's 4096)")
+    ap.add_argument("--cfg3-seconds", type=float, default=2.5, help="device time the cfg3 MCMC leg aims for")
+    ap.add_argument("--no-mcmc", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline likelihood leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -179,6 +251,7 @@ def main():
     import torch
     import torch.distributed as dist
     from covidcurve_b200 import _lib
+    from covidcurve_b200 import dist as ccdist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -195,7 +268,6 @@ def main():
             numa = "cpus %d..%d" % (min(os.sched_getaffinity(0)), max(os.sched_getaffinity(0)))
         except Exception as e:  # affinity is an optimisation, never a requirement
             numa = "unset (%s)" % type(e).__name__
-    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -204,21 +276,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op="max"):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}[op])
         return float(t.item())
 
     spec, truth = synth.make_spec("cfg3")
     d, V = spec.d, args.vectors
     model = _lib.Model(spec, device=local_rank)
-    theta = synth.random_theta(spec, V, seed=synth.SEED_THETA + rank, bad_frac=0.01)
-    h_theta = torch.from_numpy(np.ascontiguousarray(theta.T)).pin_memory()       # SoA [d][V], pinned
-    h_out = torch.empty(V, dtype=torch.float64).pin_memory()
-    d_theta = h_theta.to(dev)
-    d_out = torch.empty(V, dtype=torch.float64, device=dev)
     # a real (non-default) torch stream: the library launches on the stream handle it is given, and torch's CUDA events
     # only see the stream they are recorded on
     tstream = torch.cuda.Stream(device=dev)
@@ -226,71 +293,90 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    def step_device():
-        model.loglike_ptr(d_theta.data_ptr(), V, V, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+    def timed_device(d_theta, d_out, n, steps):
+        """K back-to-back device-resident passes; returns ms (max over ranks)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model.loglike_ptr(d_theta.data_ptr(), n, n, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+        e1.record()
+        barrier()
+        return reduce_ranks(e0.elapsed_time(e1))
 
-    def step_host():
-        model.loglike_ptr(h_theta.data_ptr(), V, V, h_out.data_ptr(), _lib.CC_MEM_HOST, 0)
-
-    # ---------------------------------------------------------------- device-resident leg (value)
+    # ---------------------------------------------------------------- strong split of the V vectors (value)
+    theta_all = synth.random_theta(spec, V, seed=synth.SEED_THETA, bad_frac=0.01)      # the same V vectors on every rank
+    off, Vs = ccdist.shard_vectors(V, world, rank)
+    theta = theta_all[off:off + Vs]
+    h_theta = torch.from_numpy(np.ascontiguousarray(theta.T)).pin_memory()       # SoA [d][Vs], pinned
+    h_out = torch.empty(Vs, dtype=torch.float64).pin_memory()
+    d_theta = h_theta.to(dev)
+    d_out = torch.empty(Vs, dtype=torch.float64, device=dev)
     for _ in range(args.warmup):
-        step_device()
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
+        model.loglike_ptr(d_theta.data_ptr(), Vs, Vs, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+    clocks = ClockSampler(local_rank).start()
+    ms_total = timed_device(d_theta, d_out, Vs, args.steps)
     clk = clocks.stop()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = V * args.steps / (ms_total * 1e-3)
     # per-launch kernel time (CUDA events on the launching stream, recorded inside cc_loglike_batch)
+    kernel_ms = []
     for _ in range(3):
-        step_device()
+        model.loglike_ptr(d_theta.data_ptr(), Vs, Vs, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
         torch.cuda.synchronize()
         kernel_ms.append(model.last_kernel_ms()[0])
     kern_ms = float(np.mean(kernel_ms))
-    value = V * world * args.steps / (ms_total * 1e-3)
+    launches_per_step = model.last_kernel_ms()[1]
     ll = d_out.cpu().numpy()
     full_frac = float(np.mean(ll != _lib.CC_OVERFLO_LOGLIKE))
 
-    # ---------------------------------------------------------------- same kernel on posterior-like vectors (truth x (1 + 2% noise)):
+    # ---------------------------------------------------------------- weak figure: V vectors on every GPU (N > 1)
+    weak = None
+    if world > 1:
+        thw = synth.random_theta(spec, V, seed=synth.SEED_THETA + rank, bad_frac=0.01) if rank else theta_all
+        d_thw = torch.from_numpy(np.ascontiguousarray(thw.T)).to(dev)
+        d_outw = torch.empty(V, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            model.loglike_ptr(d_thw.data_ptr(), V, V, d_outw.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+        msw = timed_device(d_thw, d_outw, V, args.steps)
+        weak = {"value": V * world * args.steps / (msw * 1e-3), "unit": UNIT, "vectors_per_gpu_per_step": V, "ms_per_step": msw / args.steps}
+        del d_thw, d_outw, thw
+
+    # ---------------------------------------------------------------- posterior-like vectors (truth x (1 + 2% noise)), N = 1 only:
     # the regime an MCMC actually visits (the box-uniform draws above spend ~1/9 of the vectors in sod < 0.115, where the
     # gamma table falls back to the general incomplete-gamma algorithm)
-    near = synth.random_theta(spec, V, seed=synth.SEED_THETA + 1000 + rank, bad_frac=0.0, near_truth=synth.true_theta(spec, truth), jitter=0.02)
-    d_near = torch.from_numpy(np.ascontiguousarray(near.T)).to(dev)
-    d_out2 = torch.empty(V, dtype=torch.float64, device=dev)
-    for _ in range(2):
-        model.loglike_ptr(d_near.data_ptr(), V, V, d_out2.data_ptr(), _lib.CC_MEM_DEVICE, stream)
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(args.steps):
-        model.loglike_ptr(d_near.data_ptr(), V, V, d_out2.data_ptr(), _lib.CC_MEM_DEVICE, stream)
-    p1.record()
-    barrier()
-    value_post = V * world * args.steps / (max_over_ranks(p0.elapsed_time(p1)) * 1e-3)
-    del d_near, near
+    value_post = None
+    if world == 1:
+        near = synth.random_theta(spec, V, seed=synth.SEED_THETA + 1000, bad_frac=0.0, near_truth=synth.true_theta(spec, truth), jitter=0.02)
+        d_near = torch.from_numpy(np.ascontiguousarray(near.T)).to(dev)
+        d_out2 = torch.empty(V, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            model.loglike_ptr(d_near.data_ptr(), V, V, d_out2.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+        value_post = V * args.steps / (timed_device(d_near, d_out2, V, args.steps) * 1e-3)
+        del d_near, near, d_out2
 
     # ---------------------------------------------------------------- end-to-end leg (host buffers through the C ABI)
-    for _ in range(max(1, args.warmup // 2)):
-        step_host()
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
+    def timed_host(theta_ptr, out_ptr, steps):
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            model.loglike_ptr(theta_ptr, Vs, Vs, out_ptr, _lib.CC_MEM_HOST, 0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - wall0
+        barrier()
+        return reduce_ranks(dt)
+
     e2e_steps = max(2, args.steps // 2)
-    wall0 = time.perf_counter()
-    t0.record()
-    for _ in range(e2e_steps):
-        step_host()
-    t1.record()
-    barrier()
-    wall = max_over_ranks(time.perf_counter() - wall0)
-    e2e_value = V * world * e2e_steps / wall
+    timed_host(h_theta.data_ptr(), h_out.data_ptr(), max(1, args.warmup // 2))
+    e2e_value = V * e2e_steps / timed_host(h_theta.data_ptr(), h_out.data_ptr(), e2e_steps)
     assert np.array_equal(h_out.numpy(), ll), "host path and device path must agree bit for bit"
+    # the same call from PAGEABLE memory (plain numpy arrays, as an R caller's REAL(theta) would be): the library stages it
+    # through its own pinned ring
+    p_theta = np.ascontiguousarray(theta.T).copy()
+    p_out = np.empty(Vs)
+    timed_host(p_theta.ctypes.data, p_out.ctypes.data, 1)
+    e2e_pageable = V * e2e_steps / timed_host(p_theta.ctypes.data, p_out.ctypes.data, e2e_steps)
+    assert np.array_equal(p_out, ll), "pageable host path and device path must agree bit for bit"
+    del p_theta
     # the PCIe ceiling of that leg: the same pinned buffer copied alone (reported, not part of any timed region above)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d_theta.copy_(h_theta, non_blocking=True)
@@ -299,30 +385,118 @@ def main():
         d_theta.copy_(h_theta, non_blocking=True)
     c1.record()
     torch.cuda.synchronize()
-    h2d_gbs = 3 * d * V * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    h2d_gbs = 3 * d * Vs * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
 
-    # ---------------------------------------------------------------- MCMC leg (configs[2]: 64 chains x 50 rungs per GPU)
-    mcmc = None
-    if args.mcmc_iters > 0:
-        chains, rungs = truth["chains"], truth["rungs"]
-        init = np.tile(synth.true_theta(spec, truth), (chains, 1))
-        settle = args.mcmc_settle  # untimed iterations that let the Robbins-Monro bandwidths settle (bw starts at 1)
-        burn = args.mcmc_iters + settle + 4
-        mc = _lib.Mcmc(model, burnin=burn, samples=0, rungs=rungs, chains=chains, chain_offset=rank * chains, seed=synth.SEED_MCMC,
-                       record_rungs=False, init=init)
-        mc.advance(settle)
+    # ---------------------------------------------------------------- MCMC legs
+    def oracle_check(spec_, out, n_max):
+        """final cold-rung states re-evaluated by the CPU oracle (rank 0): max relative error of the recorded log-likelihoods"""
+        from oracle.oracle import Oracle
+        th = out["theta"][:n_max, 0, -1, :]
+        chk = Oracle(spec_).loglike(th, nthreads=min(host_threads(), 16))
+        got = out["loglike"][:n_max, 0, -1]
+        bad = (chk == _lib.CC_OVERFLO_LOGLIKE) | (got == _lib.CC_OVERFLO_LOGLIKE)
+        rel = np.abs(got[~bad] - chk[~bad]) / np.abs(chk[~bad])
+        return {"states": int(len(th)), "max_rel_err_vs_oracle": float(rel.max()) if rel.size else 0.0,
+                "failure_value_mismatches": int(np.sum(bad & (chk != got)))}
+
+    mcmc = mcmc3 = collective = None
+    if not args.no_mcmc:
+        # ---- cfg3: 64 chains x 50 rungs on ONE GPU (BASELINE configs[2]); every rank runs its own 64 chains when N > 1
+        chains3, rungs3 = truth["chains"], truth["rungs"]
+        init3 = np.tile(synth.true_theta(spec, truth), (chains3, 1))
+        settle3, probe3 = 100, 50
+        cap3 = 6000
+        mc = _lib.Mcmc(model, burnin=settle3 + probe3 + cap3 + 2, samples=0, rungs=rungs3, chains=chains3, chain_offset=rank * chains3,
+                       seed=synth.SEED_MCMC, record_rungs=False, init=init3, thin=50)
+        mc.advance(settle3)               # untimed: lets the Robbins-Monro bandwidths settle (bw starts at 1)
+        mc.advance(probe3)
+        it3 = int(min(cap3, max(100, args.cfg3_seconds * 1e3 / (mc.last_advance_ms / probe3))))
+        clocks = ClockSampler(local_rank).start()
         barrier()
-        m0 = time.perf_counter()
-        mc.advance(args.mcmc_iters)
-        torch.cuda.synchronize()
-        mdt = max_over_ranks(time.perf_counter() - m0)
+        mc.advance(it3)
+        ms3 = reduce_ranks(mc.last_advance_ms)
+        clk3 = clocks.stop()
         barrier()
-        particles = chains * rungs * world
-        mcmc = {"iter_per_sec_all_chains_x_rungs": particles * args.mcmc_iters / mdt, "chains_per_gpu": chains, "rungs": rungs,
-                "iterations_timed": args.mcmc_iters, "loglike_evals_per_sec": particles * args.mcmc_iters * d / mdt,
-                "ms_per_iteration": mdt / args.mcmc_iters * 1e3, "settle_iterations": settle,
-                "workload": "cfg3: 64 chains x 50 rungs per GPU, d=34 (one iteration = d single-site updates + coupling pass)"}
+        P3 = chains3 * rungs3 * world
+        mcmc3 = {"iter_per_sec_all_chains_x_rungs": P3 * it3 / (ms3 * 1e-3), "chains_per_gpu": chains3, "rungs": rungs3,
+                 "iterations_timed": it3, "device_seconds": ms3 * 1e-3, "loglike_evals_per_sec": P3 * it3 * d / (ms3 * 1e-3),
+                 "ms_per_iteration": ms3 / it3, "settle_iterations": settle3 + probe3, "sm_mhz": clk3.get("sm_mhz"),
+                 "sm_min_mhz_over_ranks": reduce_ranks(clk3.get("sm_min_mhz") or 0.0, "min"), "reasons": clk3.get("reasons"),
+                 "timing": "CUDA events on the library's stream around the %d iterations (2 launches each), max over ranks" % it3,
+                 "workload": "cfg3: 64 chains x 50 rungs per GPU, d=34 (one iteration = d single-site updates + coupling pass)"}
+        if rank == 0:
+            mcmc3["check"] = oracle_check(spec, mc.fetch(), 64)
         mc.close()
+
+        # ---- cfg4: 4096 chains x 64 rungs sharded over the ranks (BASELINE configs[3])
+        spec4, truth4 = synth.make_spec("cfg4")
+        model4 = _lib.Model(spec4, device=local_rank)
+        chains4 = args.mcmc_chains or truth4["chains"]
+        rungs4 = truth4["rungs"]
+        c_off, c_loc = ccdist.shard_chains(chains4, world, rank)
+        it4 = args.mcmc_iters if args.mcmc_iters > 0 else int(min(200, max(12, 25 * world)))
+        settle4 = args.mcmc_settle
+        init4 = np.tile(synth.true_theta(spec4, truth4), (c_loc, 1))
+        # the timed iterations are the sampling phase (their cold-rung draws are what the collective gathers)
+        mc4 = _lib.Mcmc(model4, burnin=settle4 + 1, samples=it4, rungs=rungs4, chains=c_loc, chain_offset=c_off, seed=synth.SEED_MCMC,
+                        record_rungs=False, init=init4, GTI_pow=3.0)
+        mc4.advance(settle4)
+        clocks = ClockSampler(local_rank).start()
+        barrier()
+        mc4.advance(it4)
+        ms4 = reduce_ranks(mc4.last_advance_ms)
+        clk4 = clocks.stop()
+        barrier()
+        P4 = chains4 * rungs4
+        mcmc = {"iter_per_sec_all_chains_x_rungs": P4 * it4 / (ms4 * 1e-3), "chains": chains4, "rungs": rungs4, "chains_per_gpu": c_loc,
+                "iterations_timed": it4, "device_seconds": ms4 * 1e-3, "loglike_evals_per_sec": P4 * it4 * spec4.d / (ms4 * 1e-3),
+                "ms_per_iteration": ms4 / it4, "settle_iterations": settle4, "scaling": "strong (chains sharded, no per-iteration communication)",
+                "sm_mhz": clk4.get("sm_mhz"), "sm_min_mhz_over_ranks": reduce_ranks(clk4.get("sm_min_mhz") or 0.0, "min"),
+                "reasons": clk4.get("reasons"), "power_w_max": clk4.get("power_w_max"),
+                "workload": "cfg4: 17 age bands x 400 days, d=48, %d chains x %d rungs sharded over %d GPU(s)" % (chains4, rungs4, world)}
+        out4 = mc4.fetch() if rank == 0 else None
+        if rank == 0:
+            mcmc["check"] = oracle_check(spec4, out4, 32)
+
+        # ---- the run's only collective: all-gather of the cold-rung SAMPLING draws (device tensors, NCCL) + R-hat
+        rows = mc4.rows
+        draws = ccdist.draws_tensor(mc4, dev)[:, 0, rows - it4:rows, :].contiguous()      # [chains_local, it4, d] in HBM
+        torch.cuda.synchronize()
+        gathered = ccdist.allgather_draws(draws, chains4)                                     # warm-up (NCCL connection set-up)
+        rh_red = ccdist.rhat_allreduce(draws, chains4)
+        reps, ag_ms, ar_ms = 5, [], []
+        for _ in range(reps):
+            barrier()
+            g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            g0.record()
+            gathered = ccdist.allgather_draws(draws, chains4)
+            g1.record()
+            rh_red = ccdist.rhat_allreduce(draws, chains4)
+            g2.record()
+            torch.cuda.synchronize()
+            ag_ms.append(reduce_ranks(g0.elapsed_time(g1)))
+            ar_ms.append(reduce_ranks(g1.elapsed_time(g2)))
+        rh_gat = ccdist.rhat_torch(gathered)
+        total_bytes = gathered.numel() * 8
+        ag = float(np.median(ag_ms))
+        collective = {
+            "backend": "nccl" if world > 1 else "none (single process: the gather is the identity)", "world": world,
+            "allgather": {"what": "cold-rung sampling draws [chains, iterations, d] f64, device tensors (zero-copy view of the run state)",
+                          "shape": list(gathered.shape), "bytes_total": total_bytes, "bytes_per_rank": draws.numel() * 8, "ms": ag,
+                          "algbw_GBps": total_bytes / (ag * 1e-3) / 1e9, "busbw_GBps": total_bytes * (world - 1) / world / (ag * 1e-3) / 1e9},
+            "rhat_allreduce": {"what": "3 x d per-chain moment sums, one all-reduce (includes the local reductions over the draws)",
+                               "bytes": 3 * spec4.d * 8, "ms": float(np.median(ar_ms))},
+            "rhat_max_abs_diff_allreduce_vs_gathered": float((rh_red - rh_gat).abs().max().item()),
+            "rhat_median": float(rh_gat.median().item()), "timing": "CUDA events, median of %d, max over ranks" % reps}
+        if rank == 0:
+            from covidcurve_b200.summaries import rhat_per_parameter
+            host = rhat_per_parameter(gathered.cpu().numpy())
+            collective["rhat_max_abs_diff_device_vs_host_numpy"] = float(np.max(np.abs(host - rh_gat.cpu().numpy())))
+            # the gathered block of rank 0's own chains is bit for bit what rank 0 recorded
+            collective["gathered_equals_local"] = bool(np.array_equal(gathered[:c_loc].cpu().numpy(), out4["theta"][:, 0, rows - it4:rows, :]))
+        del gathered, draws
+        mc4.close()
+        model4.close()
 
     # ---------------------------------------------------------------- roofline + CPU baseline (rank 0)
     if rank == 0:
@@ -330,23 +504,21 @@ def main():
         dmma_tf, _, _ = _lib.dmma_probe(local_rank, 8192, 0)
         peak_tf = max(dfma_tf, dmma_tf)
         falg = f_alg(spec)
-        alg_bytes = (8 * d + 8) * V
-        flops_per_launch = falg * V * full_frac
-        achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12
+        alg_bytes = (8 * d + 8) * Vs
+        achieved = falg * Vs * full_frac / (kern_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_src = measured_traffic()
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-            # (profiles/r1_phase2_box_metrics.txt: 170.3 MB read + 13.5 MB written for 262 144 box-uniform evaluations = 701 B per
-            # evaluation: the SoA record handed over by the thread-per-vector pass, its result fields, the permutation)
-            "traffic": 701.0 * V, "traffic_source": "ncu --set full capture of loglike_phase2_kernel at 262 144 vectors, per-evaluation bytes x vectors of this launch",
+            "traffic": traffic["bytes_per_eval"] * Vs if traffic else None, "traffic_source": traffic_src,
             "algorithmic_bytes": float(alg_bytes),
-            "kernel": "loglike_phase2_kernel (the per-day pass; kernel_ms covers the whole 5-launch pipeline of one cc_loglike_batch call)", "kernel_ms": kern_ms, "flops_per_eval": falg, "full_eval_fraction": full_frac,
+            "kernel": "loglike_phase2_kernel (the per-day pass; kernel_ms covers the whole pipeline of one cc_loglike_batch call)",
+            "kernel_ms": kern_ms, "vectors_per_launch": Vs, "flops_per_eval": falg, "full_eval_fraction": full_frac,
             "peak_source": "max of cc_fp64_peak_probe (register-resident DFMA chains: %.2f) and cc_dmma_probe (mma.sync m8n8k4 f64: %.2f), measured "
                            "live in this run; MEASURED_PEAKS.json has no FP64 entry" % (dfma_tf, dmma_tf),
             "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -355,38 +527,46 @@ def main():
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            rate, n, dt = cpu_reference_rate(spec, theta, args.cpu_seconds, cores)
             from oracle.oracle import Oracle
-            chk = Oracle(spec).loglike(theta[:n], nthreads=cores)
+            o = Oracle(spec)
+            cores = host_threads()
+            rate, n, dt, chk = cpu_loglike_rate(o, theta, args.cpu_seconds, cores)
+            rate1, n1, dt1, _ = cpu_loglike_rate(o, theta, 4.0, 1)
             bad = (chk == _lib.CC_OVERFLO_LOGLIKE) | (ll[:n] == _lib.CC_OVERFLO_LOGLIKE)
             relv = np.zeros(n)
             relv[~bad] = np.abs(chk[~bad] - ll[:n][~bad]) / np.abs(chk[~bad])
             mism = bad & (chk != ll[:n])
-            # sod in [0.021, 0.0235] is the band where expected counts become subnormal and the reference's gradual-underflow
-            # semantics decide the value; reported separately because it is the hardest part of the box
-            sod = theta[:n, spec.index("sod")]
-            band = (sod > 0.021) & (sod < 0.0235)
+            worst = np.argsort(relv)[-3:][::-1]
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "first %d of the step's vectors, %.1f s, %d threads (g++ -O2 restatement of the reference; the reference "
                              "itself needs R/Rcpp/libRmath, absent here)" % (n, dt, cores),
-                   "max_rel_err_gpu_vs_cpu": float(relv[~band].max()), "failure_value_mismatches": int(mism[~band].sum()),
-                   "p999_rel_err_gpu_vs_cpu": float(np.quantile(relv, 0.999)),
-                   "subnormal_band": {"sod": [0.021, 0.0235], "vectors": int(band.sum()), "max_rel_err": float(relv[band].max()) if band.any() else 0.0,
-                                      "failure_value_mismatches": int(mism[band].sum())}}
+                   "value_1_core": rate1, "sample_1_core": "first %d vectors, %.1f s, 1 thread" % (n1, dt1),
+                   "max_rel_err_gpu_vs_cpu": float(relv.max()), "failure_value_mismatches": int(mism.sum()),
+                   "p999_rel_err_gpu_vs_cpu": float(np.quantile(relv, 0.999)), "vectors_above_1e-10": int(np.sum(relv > 1e-10)),
+                   "worst_vectors": [{"index": int(i), "rel_err": float(relv[i]), "sod": float(theta[i, spec.index("sod")]),
+                                      "mod": float(theta[i, spec.index("mod")])} for i in worst]}
+            if not args.no_mcmc:
+                cpu["mcmc"] = {"cfg3_all_cores": cpu_mcmc_rate("cfg3", cores, 6.0), "cfg3_1_core": cpu_mcmc_rate("cfg3", 1, 5.0),
+                               "cfg4_all_cores": cpu_mcmc_rate("cfg4", cores, 8.0),
+                               "note": "oracle port of drjacoby's loop (one chain per thread, 4 rungs): chain-rung iterations/s, the unit of `mcmc`"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "cfg5: likelihood-only, 10 age bands x 300 days x 5 knots x 3 serosurveys, binomial (d=34)",
-                       "vectors_per_gpu_per_step": V, "layout": "SoA theta[d][V]", "l2": "inputs larger than L2 (%.0f MB per step)" % (d * V * 8 / 1e6),
-                       "full_eval_fraction": full_frac},
+            "config": {"workload": WORKLOAD, "vectors_per_step": V, "vectors_per_gpu_per_step": Vs, "layout": "SoA theta[d][V]",
+                       "l2": "inputs larger than L2 (%.0f MB per GPU per step)" % (d * Vs * 8 / 1e6) if d * Vs * 8 > 126e6 else
+                             "inputs of %.0f MB per GPU per step: the likelihood reads each value once, L2 residency of theta is irrelevant "
+                             "(FP64-bound, < 1 %% of HBM bandwidth)" % (d * Vs * 8 / 1e6),
+                       "full_eval_fraction": full_frac, "split": "V vectors split evenly over the ranks (SURVEY.md 8e), no collective"},
+            "weak": weak,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": d * V * 8, "d2h_bytes_per_step": V * 8, "steps": e2e_steps,
-                    "h2d_gbs_measured": h2d_gbs, "h2d_bound": h2d_gbs * 1e9 / (d * 8) * world, "cpu_affinity": numa},
-            "gpu_launches": args.steps * 5,  # phase-1 pass, bucket offsets, scatter, phase-2 pass, phase-3 pass per step
-            "posterior_like": {"value": value_post, "unit": UNIT, "frac_of_fp64_peak": value_post * falg / 1e12 / peak_tf,
-                               "vectors": "truth x (1 + 0.02 N(0,1)), clipped to the box"},
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "mcmc": mcmc,
+                    "h2d_gbs_measured_per_rank": h2d_gbs, "h2d_bound": h2d_gbs * 1e9 / (d * 8) * world, "cpu_affinity": numa,
+                    "pageable": {"value": e2e_pageable, "unit": UNIT,
+                                 "note": "caller buffers in pageable memory, staged by the library through its pinned ring"}},
+            "gpu_launches": args.steps * launches_per_step,
+            "posterior_like": None if value_post is None else {"value": value_post, "unit": UNIT, "frac_of_fp64_peak": value_post * falg / 1e12 / peak_tf,
+                                                                "vectors": "truth x (1 + 0.02 N(0,1)), clipped to the box"},
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "mcmc": mcmc, "mcmc_cfg3": mcmc3, "collective": collective,
         }
         print(json.dumps(out))
     if world > 1:

@@ -69,6 +69,7 @@ SYMBOLS = {
     "cc_curves_batch": (C.c_int, [_vp, c_dp, C.c_int64, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
     "cc_mcmc_create": (C.c_int, [_vp, C.POINTER(McmcOpts), C.POINTER(_vp)]),
     "cc_mcmc_advance": (C.c_int, [_vp, C.c_int32]),
+    "cc_mcmc_last_advance_ms": (C.c_int, [_vp, c_dp]),
     "cc_mcmc_iterations": (C.c_int64, [_vp]),
     "cc_mcmc_rows": (C.c_int64, [_vp]),
     "cc_mcmc_fetch": (C.c_int, [_vp, c_dp, c_dp, c_dp, c_ip]),
@@ -261,6 +262,13 @@ class Mcmc:
 
     def advance(self, n_iter: int):
         check(self.L.cc_mcmc_advance(self.h, n_iter))
+
+    @property
+    def last_advance_ms(self):
+        """Device time (CUDA events on the library's stream) of the last advance()."""
+        ms = C.c_double()
+        check(self.L.cc_mcmc_last_advance_ms(self.h, C.byref(ms)))
+        return ms.value
 
     @property
     def iterations(self):

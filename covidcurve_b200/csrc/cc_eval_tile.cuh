@@ -411,10 +411,18 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
         const double tnext = __shfl_down_sync(0xffffffffu, incl, o);
         if (lane + o < 32) incl += tnext;
       }
-      double run = QT + (incl - loc);
+      // masses of all later lanes = the next lane's inclusive sum.  (NOT incl - loc: where this lane holds the bulk of the
+      // distribution and the later lanes only the far tail, that difference cancels - it cost six digits of the upper tail
+      // at the lane boundary and, through the rounding of 1 - Q, one ulp of the reference's lower-tail value.)
+      double excl = __shfl_down_sync(0xffffffffu, incl, 1);
+      if (lane == 31) excl = 0.0;
+      double run = QT + excl;
       for (int k = hi - 1; k >= lo; k--)
         if (k > km) {
           run += P[k];
+#ifdef CC_DEBUG_RAWQ  // developer build: the unrounded upper tail of vector 0 instead of the hazard prefix sums
+          if (m.debug_dump && blockIdx.x == 0 && (threadIdx.x >> 5) == 0) m.debug_dump[3 * T + k] = run;
+#endif
           P[k] = 1.0 - run;
         }
       if (lane == 0) P[T] = 1.0 - QT;
@@ -491,7 +499,8 @@ __device__ inline void tile_sero_prefix(const KModel& m, const RecLayout& L, con
     const double tprev = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += tprev;
   }
-  double run = incl - loc;
+  double run = __shfl_up_sync(0xffffffffu, incl, 1);  // sum of the earlier lanes, without the cancellation of incl - loc
+  if (lane == 0) run = 0.0;
   for (int u = lo; u < hi; u++) {
     w.sk[u] = run;
     run += haz[u];
@@ -725,7 +734,9 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   if (m.debug_dump && e == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
     for (int j = lane; j < T; j += 32) {
       m.debug_dump[j] = w.gs[7 + j];
+#ifndef CC_DEBUG_RAWQ
       m.debug_dump[3 * T + j] = w.sk[min(j, m.M)];
+#endif
     }
   __syncwarp();
   stage_conv<NT>(m, w.xs, w.gs, w.auc, conv_lag_blocks(m, L, w.rec));

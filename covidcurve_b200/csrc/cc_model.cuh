@@ -66,6 +66,9 @@ struct cc_model {
   cudaStream_t stream3 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_slot0 = nullptr;  // end of the last device-pointer call (serialises calls that arrive on different streams)
+  cudaStream_t slot0_stream = nullptr;
+  bool slot0_used = false;
   double last_ms = 0.0;
   int last_launches = 0;
   // host staging (pinned) + device staging for CC_MEM_HOST calls

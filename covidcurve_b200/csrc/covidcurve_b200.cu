@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/covidcurve_b200.h"
@@ -100,7 +101,11 @@ constexpr int kSweepWarps = CC_SWEEP_WARPS;
 // Grouping by regime keeps the warps of a CTA on the same code path (small gamma table / large table / general algorithm /
 // no per-day work at all) and lets the launch start with the expensive vectors (history: profiles/r1_summary.md).
 constexpr int kNumKeys = 8;       // histogram slots; keys 0..5 are used, slot 6 is the phase-2 tile ticket
-constexpr int kPhase2Tile = 8;    // vectors per dynamically fetched tile of pass C
+constexpr int kLoglikeLaunches = 5;  // kernels per cc_loglike_batch pipeline (launch_loglike)
+#ifndef CC_P2_TILE
+#define CC_P2_TILE 2
+#endif
+constexpr int kPhase2Tile = CC_P2_TILE;    // vectors per warp of a dynamically fetched CTA tile of pass C
 
 template <int NT>
 __global__ void __launch_bounds__(128) loglike_phase1_kernel(const KModel m, const double* __restrict__ theta, long long n, long long ld,
@@ -980,6 +985,7 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
   for (int q = 0; q < 3 && e == cudaSuccess; q++) e = cudaEventCreateWithFlags(&m->ev_stage[q], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_slot0, cudaEventDisableTiming);
   // opt in to large dynamic shared memory once
   m->nt = pick_nt(T);
   if (e == cudaSuccess && m->nt < 0) {
@@ -1050,6 +1056,7 @@ extern "C" void cc_model_destroy(cc_model* m) {
     if (m->ev_stage[q]) cudaEventDestroy(m->ev_stage[q]);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->ev_slot0) cudaEventDestroy(m->ev_slot0);
   if (m->stream) cudaStreamDestroy(m->stream);
   if (m->stream2) cudaStreamDestroy(m->stream2);
   if (m->stream3) cudaStreamDestroy(m->stream3);
@@ -1134,28 +1141,91 @@ static int ensure_stage(cc_model* m, size_t theta_bytes, size_t out_bytes) {
 
 typedef int (*launch_fn)(cc_model*, const double*, long long, long long, double*, cudaStream_t, int);
 
-// Host-buffer path: column chunks are copied H2D (2-D copy: d rows of `chunk` doubles), evaluated and copied back,
-// triple-buffered over three streams so that the copy engine never waits for a staging slot: while chunk k computes,
-// chunk k+1 is uploaded and chunk k+2 can already start uploading (with two slots the upload of k+2 had to wait for the
-// kernels of k, which cost 25 % when four ranks share the host's PCIe bandwidth).  Pinned caller memory gives true overlap;
-// pageable memory still works (the driver stages it).
+// true when `p` is page-locked (or managed) host memory the copy engine can read directly
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// row-wise host copy dst[r * dld + 0..n) <- src[r * sld + 0..n), r < rows, on a few threads (a single thread moves ~10 GB/s,
+// less than the GPU consumes: 272-byte vectors at 80 M evaluations/s are 22 GB/s)
+static void host_copy_rows(double* dst, size_t dld, const double* src, size_t sld, size_t n, int rows) {
+  const size_t bytes = n * sizeof(double) * (size_t)rows;
+  int nth = (int)std::min<size_t>(4, std::max<size_t>(1, bytes >> 22));
+  nth = std::min(nth, std::max(1, rows));
+  auto work = [&](int t) {
+    for (int r = t; r < rows; r += nth) std::memcpy(dst + (size_t)r * dld, src + (size_t)r * sld, n * sizeof(double));
+  };
+  if (nth == 1) {
+    work(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nth; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto& t : th) t.join();
+}
+
+// Host-buffer path: column chunks are copied H2D (d rows of `chunk` doubles), evaluated and copied back, triple-buffered
+// over three streams so that the copy engine never waits for a staging slot: while chunk k computes, chunk k+1 is uploaded
+// and chunk k+2 can already start uploading (with two slots the upload of k+2 had to wait for the kernels of k, which cost
+// 25 % when four ranks share the host's PCIe bandwidth).
+//   * page-locked caller memory (cudaHostAlloc / cudaHostRegister, torch pin_memory) is read and written by the copy engine
+//     in place (2-D copies);
+//   * PAGEABLE caller memory (malloc, an R vector's REAL()) is staged through the library's own pinned ring: the calling
+//     thread packs chunk k+1 into a pinned slot while the GPU works on chunk k, and unpacks finished outputs.
 static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long long n, long long ld, double* out) {
   const int d = m->k.d;
   constexpr int kSlots = 3;
+  const bool pinned_in = host_ptr_is_pinned(theta), pinned_out = host_ptr_is_pinned(out);
   // Chunk sizes grow geometrically (64k, 128k, ... up to 512k vectors): only the first chunk's upload and the last
   // chunk's download are exposed, so they are kept small, while the bulk runs in large launches (measured on B200 at
-  // 2^20 vectors: fixed 128k chunks 56.8 M evals/s, 256k 58.6, 512k 60.1; profiles/r1_summary.md)
-  long long cmax = 1 << 19;
+  // 2^20 vectors: fixed 128k chunks 56.8 M evals/s, 256k 58.6, 512k 60.1; profiles/r1_summary.md).  The pinned ring of the
+  // pageable path is capped at 128k vectors per slot (d x 1 MB of page-locked memory each).
+  long long cmax = pinned_in ? (1 << 19) : (1 << 17);
   if (const char* e = std::getenv("CC_HOST_CHUNK")) cmax = std::max<long long>(1024, (std::atoll(e) + 1023) & ~1023LL);  // developer tuning
   cmax = std::min<long long>(cmax, (n + 1023) & ~1023LL);
   int rc = ensure_stage(m, (size_t)kSlots * d * cmax * sizeof(double), (size_t)kSlots * cmax * sizeof(double));
   if (rc) return rc;
+  const size_t pin_slot = (size_t)(d + 1) * cmax;  // doubles: [d][cmax] parameters, then [cmax] outputs
+  if (!pinned_in || !pinned_out) {
+    const size_t need = (size_t)kSlots * pin_slot * sizeof(double);
+    if (m->h_pin_bytes < need) {
+      if (m->h_pin) cudaFreeHost(m->h_pin);
+      m->h_pin = nullptr;
+      m->h_pin_bytes = 0;
+      CC_CUDA(cudaHostAlloc((void**)&m->h_pin, need, cudaHostAllocDefault));
+      m->h_pin_bytes = need;
+    }
+  }
   if (fn == launch_loglike)  // size the work slots for the largest chunk now: growing them mid-pipeline would synchronise the device
     for (int slot = 1; slot <= kSlots; slot++)
       if ((rc = ensure_work(m, slot, std::min(cmax, n)))) return rc;
   cudaStream_t st[kSlots] = {m->stream, m->stream2, m->stream3};
-  CC_CUDA(cudaEventRecord(m->ev0, st[0]));
+  // on any failure: let the copies already queued into / out of caller memory finish before the caller sees the error
+  auto bail = [&](int code) {
+    for (int j = 0; j < kSlots; j++) cudaStreamSynchronize(st[j]);
+    return code;
+  };
+#define CC_CUDA_BAIL(expr)                                                                                 \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) return bail(fail(CC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
+  } while (0)
+  CC_CUDA_BAIL(cudaEventRecord(m->ev0, st[0]));
   m->last_launches = 0;
+  struct Pending { long long c0 = 0, cn = 0; bool busy = false; } pend[kSlots];
+  auto drain = [&](int q) -> int {  // outputs of the chunk that last used slot q: pinned slot -> caller memory
+    if (!pend[q].busy) return CC_OK;
+    CC_CUDA_BAIL(cudaEventSynchronize(m->ev_stage[q]));
+    if (!pinned_out) std::memcpy(out + pend[q].c0, m->h_pin + (size_t)q * pin_slot + (size_t)d * cmax, (size_t)pend[q].cn * sizeof(double));
+    pend[q].busy = false;
+    return CC_OK;
+  };
   int q = 0;
   long long chunk = std::min<long long>(cmax, 1 << 16);
   for (long long c0 = 0; c0 < n; q = (q + 1) % kSlots) {
@@ -1163,21 +1233,32 @@ static int run_host_batch(cc_model* m, launch_fn fn, const double* theta, long l
     if (n - c0 - cn < (1 << 15)) cn = std::min(n - c0, cmax);  // do not leave a sliver behind
     double* dth = m->d_stage + (size_t)q * d * cmax;
     double* dout = m->d_out + (size_t)q * cmax;
-    CC_CUDA(cudaMemcpy2DAsync(dth, (size_t)cmax * sizeof(double), theta + c0, (size_t)ld * sizeof(double),
-                              (size_t)cn * sizeof(double), (size_t)d, cudaMemcpyHostToDevice, st[q]));
+    double* hp = m->h_pin ? m->h_pin + (size_t)q * pin_slot : nullptr;
+    if ((!pinned_in || !pinned_out) && (rc = drain(q))) return rc;  // the slot's previous chunk has left the pinned ring
+    if (pinned_in) {
+      CC_CUDA_BAIL(cudaMemcpy2DAsync(dth, (size_t)cmax * sizeof(double), theta + c0, (size_t)ld * sizeof(double),
+                                     (size_t)cn * sizeof(double), (size_t)d, cudaMemcpyHostToDevice, st[q]));
+    } else {
+      host_copy_rows(hp, (size_t)cmax, theta + c0, (size_t)ld, (size_t)cn, d);
+      CC_CUDA_BAIL(cudaMemcpy2DAsync(dth, (size_t)cmax * sizeof(double), hp, (size_t)cmax * sizeof(double), (size_t)cn * sizeof(double),
+                                     (size_t)d, cudaMemcpyHostToDevice, st[q]));
+    }
     rc = fn(m, dth, cn, cmax, dout, st[q], 1 + q);
-    if (rc) return rc;
-    m->last_launches += 5;
-    CC_CUDA(cudaMemcpyAsync(out + c0, dout, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost, st[q]));
+    if (rc) return bail(rc);
+    m->last_launches += (fn == launch_loglike) ? kLoglikeLaunches : 1;
+    CC_CUDA_BAIL(cudaMemcpyAsync(pinned_out ? out + c0 : hp + (size_t)d * cmax, dout, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost, st[q]));
+    CC_CUDA_BAIL(cudaEventRecord(m->ev_stage[q], st[q]));
+    pend[q].c0 = c0; pend[q].cn = cn; pend[q].busy = true;
     c0 += cn;
     chunk = std::min<long long>(2 * chunk, cmax);
   }
-  for (int j = 1; j < kSlots; j++) {
-    CC_CUDA(cudaEventRecord(m->ev_stage[j], st[j]));
-    CC_CUDA(cudaStreamWaitEvent(st[0], m->ev_stage[j], 0));
-  }
-  CC_CUDA(cudaEventRecord(m->ev1, st[0]));
-  CC_CUDA(cudaStreamSynchronize(st[0]));
+  for (int j = 1; j < kSlots; j++)
+    if (pend[j].busy) CC_CUDA_BAIL(cudaStreamWaitEvent(st[0], m->ev_stage[j], 0));
+  CC_CUDA_BAIL(cudaEventRecord(m->ev1, st[0]));
+  for (int j = 0; j < kSlots; j++)
+    if ((rc = drain(j))) return rc;
+  CC_CUDA_BAIL(cudaStreamSynchronize(st[0]));
+#undef CC_CUDA_BAIL
   float ms = 0.f;
   CC_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
   m->last_ms = ms;
@@ -1192,11 +1273,17 @@ static int batch_call(cc_model* m, launch_fn fn, const double* theta, int64_t n,
   CC_CUDA(cudaSetDevice(m->device));
   if (mem == CC_MEM_DEVICE) {
     cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    // device-pointer calls share work slot 0 (records, regime buckets, tile ticket): a call on another stream than the
+    // previous one first waits for it, so calls on one model never overlap whatever streams the caller uses
+    if (m->slot0_used && m->slot0_stream != st) CC_CUDA(cudaStreamWaitEvent(st, m->ev_slot0, 0));
     CC_CUDA(cudaEventRecord(m->ev0, st));
     int rc = fn(m, theta, n, ld, out, st, 0);
     if (rc) return rc;
     CC_CUDA(cudaEventRecord(m->ev1, st));
-    m->last_launches = 5;
+    CC_CUDA(cudaEventRecord(m->ev_slot0, st));
+    m->slot0_used = true;
+    m->slot0_stream = st;
+    m->last_launches = (fn == launch_loglike) ? kLoglikeLaunches : 1;
     m->last_ms = -1.0;  // resolved lazily by cc_last_kernel_ms
     return CC_OK;
   }
@@ -1285,6 +1372,8 @@ struct cc_mcmc {
   size_t sweep_smem = 0;
   unsigned grid = 1;
   double* scratch = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the launches of the last cc_mcmc_advance on the library's stream
+  double last_ms = 0.0;
 };
 
 template <typename T>
@@ -1301,6 +1390,8 @@ extern "C" void cc_mcmc_destroy(cc_mcmc* s) {
   if (!s) return;
   cudaSetDevice(s->m->device);
   for (void* p : s->allocs) cudaFree(p);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
 }
 
@@ -1352,6 +1443,10 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
   if (!r) return fail(CC_E_NOMEM, "out of host memory");
   r->m = m;
   r->beta = beta;
+  if (cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess) {
+    cc_mcmc_destroy(r);
+    return fail(CC_E_CUDA, "cc_mcmc_create: cudaEventCreate failed");
+  }
   McmcState& s = r->s;
   s.d = d; s.rungs = R; s.n_chains = C; s.chain_offset = o->chain_offset;
   s.burnin = o->burnin; s.samples = o->samples; s.coupling_on = o->coupling_on ? 1 : 0;
@@ -1440,6 +1535,11 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
       cc_mcmc_destroy(r);
       return rc;
     }
+    // the memsets / copies above ran on the legacy default stream; m->stream is non-blocking and does not order behind it
+    if (cudaError_t es = cudaDeviceSynchronize(); es != cudaSuccess) {
+      cc_mcmc_destroy(r);
+      return fail(CC_E_CUDA, std::string("cc_mcmc_create: ") + cudaGetErrorString(es));
+    }
     switch (m->nt) {
 #define CC_LAUNCH(NT_) case NT_: mcmc_init_tile_kernel<NT_><<<r->grid, 32 * kWarpsPerCta, r->smem, m->stream>>>(m->k, s, r->le, r->scratch); break;
       CC_FOR_EACH_NT(CC_LAUNCH)
@@ -1475,6 +1575,7 @@ extern "C" int cc_mcmc_advance(cc_mcmc* r, int32_t n_iter) {
   McmcState& s = r->s;
   const long long total = (long long)s.burnin + s.samples;
   const unsigned P = (unsigned)(s.n_chains * s.rungs);
+  CC_CUDA(cudaEventRecord(r->ev0, m->stream));
   for (int k = 0; k < n_iter; k++) {
     if (r->iteration >= total) return fail(CC_E_STATE, "cc_mcmc_advance: burnin + samples iterations already done");
     const int it = (int)(r->iteration + 1);
@@ -1490,7 +1591,17 @@ extern "C" int cc_mcmc_advance(cc_mcmc* r, int32_t n_iter) {
     if (rc) return rc;
     r->iteration = it;
   }
+  CC_CUDA(cudaEventRecord(r->ev1, m->stream));
   CC_CUDA(cudaStreamSynchronize(m->stream));
+  float ms = 0.f;
+  CC_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+  r->last_ms = ms;
+  return CC_OK;
+}
+
+extern "C" int cc_mcmc_last_advance_ms(cc_mcmc* r, double* ms) {
+  if (!r || !ms) return fail(CC_E_INVALID, "cc_mcmc_last_advance_ms: null argument");
+  *ms = r->last_ms;
   return CC_OK;
 }
 

@@ -258,8 +258,31 @@ __device__ __forceinline__ double log1pmx(double x) {  // log(1+x) - x, accurate
   return r * (2 * y * s - x);
 }
 
-__device__ __noinline__ double ppois_asymp_upper(double x, double lambda) {
-  // upper tail of Poisson(lambda) at x (= lower tail of gamma(alph = x+1) at lambda), R's ppois_asymp(x, lambda, FALSE, FALSE)
+// log of the standard normal lower tail at x < -sqrt(32): the tail branch of R's pnorm_both() (Cody 1969, Algorithm 715
+// ANORM: rational approximation in 1/x^2, argument split at 1/16 so that exp(-x^2/2) loses no bits) on the log scale
+__device__ __forceinline__ double pnorm_log_lower_tail(double x) {
+  const double p0 = 0.21589853405795699, p1 = 0.1274011611602473639, p2 = 0.022235277870649807, p3 = 0.001421619193227893466,
+               p4 = 2.9112874951168792e-5, p5 = 0.02307344176494017303;
+  const double q0 = 1.28426009614491121, q1 = 0.468238212480865118, q2 = 0.0659881378689285515, q3 = 0.00378239633202758244,
+               q4 = 7.29751555083966205e-5;
+  const double y = fabs(x);
+  double xsq = 1.0 / (x * x);
+  double xnum = p5 * xsq, xden = xsq;
+  xnum = (xnum + p0) * xsq; xden = (xden + q0) * xsq;
+  xnum = (xnum + p1) * xsq; xden = (xden + q1) * xsq;
+  xnum = (xnum + p2) * xsq; xden = (xden + q2) * xsq;
+  xnum = (xnum + p3) * xsq; xden = (xden + q3) * xsq;
+  double temp = xsq * (xnum + p4) / (xden + q4);
+  temp = (CC_1_SQRT_2PI - temp) / y;
+  xsq = trunc(x * 16) / 16;
+  const double del = (x - xsq) * (x + xsq);
+  return (-xsq * xsq * 0.5) + (-del * 0.5) + log(temp);
+}
+
+// upper tail of Poisson(lambda) at x (= lower tail of gamma(alph = x+1) at lambda): R's ppois_asymp(x, lambda, FALSE, log_p).
+// The log form is what pgamma_raw falls back to when the plain value comes out below DBL_MIN / DBL_EPSILON (far lower tail of
+// very peaked delay distributions); it is valid for s2pt < -sqrt(32), which such a small value implies.
+__device__ __noinline__ double ppois_asymp_upper(double x, double lambda, bool log_p) {
   const double coefs_a[8] = {-1e99, 2 / 3., -4 / 135., 8 / 2835., 16 / 8505., -8992 / 12629925.,
                              -334144 / 492567075., 698752 / 1477701225.};
   const double coefs_b[8] = {-1e99, 1 / 12., 1 / 288., -139 / 51840., -571 / 2488320.,
@@ -288,9 +311,24 @@ __device__ __noinline__ double ppois_asymp_upper(double x, double lambda) {
   }
   elfb = -elfb;  // upper tail
   double f = res12 / elfb;
+  if (log_p && s2pt < -5.656854249492380195206754896838) {
+    // np = pnorm(s2pt, lower, log); dpnorm(s2pt, lower, np) = phi(s2pt) / Phi(s2pt) by the Mills-ratio series (|s2pt| > 10)
+    const double np = pnorm_log_lower_tail(s2pt);
+    const double ax = -s2pt;
+    double n_d_over_p;
+    if (ax > 10) {
+      double term = 1 / ax, sum = term, x2 = ax * ax, i = 1;
+#pragma unroll 1
+      do { term *= -i / x2; sum += term; i += 2; } while (fabs(term) > DBL_EPSILON * sum);
+      n_d_over_p = 1 / sum;
+    } else {
+      n_d_over_p = CC_1_SQRT_2PI * exp(-0.5 * ax * ax) / exp(np);
+    }
+    return np + log1p(f * n_d_over_p);
+  }
   double np = 0.5 * erfc(-s2pt * 0.70710678118654752440);  // pnorm(s2pt, lower = TRUE)
   double nd = CC_1_SQRT_2PI * exp(-0.5 * s2pt * s2pt);
-  return np + f * nd;
+  return log_p ? log(np + f * nd) : np + f * nd;
 }
 
 // continued fraction of R's pd_lower_cf (only reached for alph < 1, i.e. sod > 1)
@@ -382,7 +420,9 @@ __device__ __forceinline__ double pgamma_lower(const GammaShape& g, double x) {
     }
     res = 1 - d * sum;
   } else {
-    res = ppois_asymp_upper(alph - 1, x);
+    res = ppois_asymp_upper(alph - 1, x, false);
+    // R's pgamma_raw: a result below DBL_MIN / DBL_EPSILON is recomputed on the log scale and exponentiated once
+    if (res < DBL_MIN / DBL_EPSILON) res = exp_gradual(ppois_asymp_upper(alph - 1, x, true));
   }
   return res;
 }

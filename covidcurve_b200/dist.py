@@ -40,6 +40,12 @@ def allgather_draws(local, chains: int, group=None):
     if local.shape[0] != counts[rank]:
         raise ValueError("rank %d holds %d chains, expected %d" % (rank, local.shape[0], counts[rank]))
     width = max(counts)
+    if min(counts) == width:
+        # equal shards (the usual case: chains divisible by the GPU count): one collective straight into the result tensor -
+        # contiguous chain blocks in rank order ARE the global chain order, so no re-assembly copy is needed
+        out = torch.empty((chains,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     padded = local
     if local.shape[0] < width:
         pad = torch.zeros((width - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
@@ -65,6 +71,19 @@ def rhat_allreduce(local, chains: int, group=None):
     gmean = stats[0] / C
     W = stats[2] / C
     B = n / (C - 1) * (stats[1] - C * gmean * gmean)
+    V = (1 - 1 / n) * W + B / n
+    return torch.sqrt(V / W)
+
+
+def rhat_torch(draws):
+    """summaries.rhat_per_parameter for a torch tensor draws[chain, iteration, param] on any device (used on the gathered
+    draws where they live, i.e. in HBM)."""
+    import torch
+    C, n = draws.shape[0], draws.shape[1]
+    mean = draws.mean(dim=1)
+    var = draws.var(dim=1, unbiased=True) if n > 1 else torch.zeros_like(mean)
+    W = var.mean(dim=0)
+    B = n / (C - 1) * ((mean - mean.mean(dim=0, keepdim=True)) ** 2).sum(dim=0)
     V = (1 - 1 / n) * W + B / n
     return torch.sqrt(V / W)
 

@@ -119,9 +119,13 @@ void cc_model_destroy(cc_model* m);
  * reference, binomial.cpp:7, so it is not part of the batch call).
  *   theta : structure-of-arrays [d][ld], element (p, i) at theta[p*ld + i], i < n  (n contiguous -> coalesced)
  *   out   : [n] log-likelihoods
- *   mem   : CC_MEM_HOST (library stages through pinned memory) or CC_MEM_DEVICE (pointers on `device`)
+ *   mem   : CC_MEM_HOST or CC_MEM_DEVICE (pointers on `device`).  Host buffers are processed in column chunks on three
+ *           streams; page-locked caller memory (cudaHostAlloc / cudaHostRegister) is read and written in place by the copy
+ *           engine, pageable memory (malloc, an R vector) is staged through the library's own pinned ring.
  *   stream: cudaStream_t as void* (NULL = the library's own stream); the call is synchronous for CC_MEM_HOST and
- *           stream-ordered (asynchronous) for CC_MEM_DEVICE.
+ *           stream-ordered (asynchronous) for CC_MEM_DEVICE.  One model handle evaluates one device-pointer batch at a
+ *           time: a call on another stream than the previous one is ordered behind it (they share scratch buffers); use
+ *           one handle per stream for concurrent batches.
  */
 int cc_loglike_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* out, int mem, void* stream);
 /* Batched drop-in for logprior(params, param_i, misc) (R/Agecpp2strings.R:213). Same conventions. */
@@ -174,6 +178,8 @@ typedef struct cc_mcmc cc_mcmc; /* opaque run state, device resident */
 int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* opts, cc_mcmc** out);
 /* advance `n_iter` iterations (sweep + swap each); records draws on the device */
 int cc_mcmc_advance(cc_mcmc* s, int32_t n_iter);
+/* device time (ms, CUDA events on the library's stream) of the launches of the most recent cc_mcmc_advance */
+int cc_mcmc_last_advance_ms(cc_mcmc* s, double* ms);
 /* iterations done so far (1 after create: the initial state is iteration 1) */
 int64_t cc_mcmc_iterations(const cc_mcmc* s);
 /* number of recorded rows per (chain, recorded rung) so far */

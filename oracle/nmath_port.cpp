@@ -6,10 +6,11 @@
  * :269 (pweibull); src/natcubicspline_loglike_logit.cpp:337 (dnorm); R/Agecpp2strings.R:73-148
  * (dunif, dnorm, dbeta in the generated prior).
  *
- * PARITY UNPINNED in one corner: pnorm_std() below is 0.5 erfc(.) (and its log), not R's pnorm_both() (Cody 1969 rational
- * approximations; the coefficient tables are not in the reference tree).  In the main range the two agree to ~1e-16; they
- * differ where pgamma_raw redoes a value below 1.002e-292 that came out of ppois_asymp() in log space (gamma shapes above
- * ~33 500, i.e. sod < 0.0055): R then uses pnorm's log-tail expansion, this port log(0.5 erfc(.)) of a subnormal.
+ * pnorm: R's pnorm_both() (Cody 1969, "Rational Chebyshev approximation for the error function"; the ANORM routine of
+ * Algorithm 715, whose published coefficient tables are restated below) including its log-scale tail expansion.  pgamma_raw
+ * reaches it through ppois_asymp(); the log tail matters where a gamma-cdf value below 1.002e-292 coming out of that branch is
+ * redone in log space (gamma shapes above ~33 500, i.e. sod < 0.0055).  The tables are pinned numerically by
+ * tests/test_oracle_nmath.py: against erfc over the central range and against mpmath (50 digits) in the tails.
  */
 #include "nmath_port.h"
 
@@ -63,10 +64,97 @@ double logcf(double x, double i, double d, double eps) {
   return a2 / b2;
 }
 
+/* R's pnorm_both(): cum = P[X <= x], ccum = P[X > x] for X ~ N(0,1); i_tail 0: lower only, 1: upper only, 2: both */
+void pnorm_both(double x, double* cum, double* ccum, int i_tail, int log_p) {
+  static const double a[5] = {2.2352520354606839287, 161.02823106855587881, 1067.6894854603709582, 18154.981253343561249,
+                              0.065682337918207449113};
+  static const double b[4] = {47.20258190468824187, 976.09855173777669322, 10260.932208618978205, 45507.789335026729956};
+  static const double c[9] = {0.39894151208813466764, 8.8831497943883759412, 93.506656132177855979, 597.27027639480026226,
+                              2494.5375852903726711, 6848.1904505362823326, 11602.651437647350124, 9842.7148383839780218,
+                              1.0765576773720192317e-8};
+  static const double d[8] = {22.266688044328115691, 235.38790178262499861, 1519.377599407554805, 6485.558298266760755,
+                              18615.571640885098091, 34900.952721145977266, 38912.003286093271411, 19685.429676859990727};
+  static const double p[6] = {0.21589853405795699, 0.1274011611602473639, 0.022235277870649807, 0.001421619193227893466,
+                              2.9112874951168792e-5, 0.02307344176494017303};
+  static const double q[5] = {1.28426009614491121, 0.468238212480865118, 0.0659881378689285515, 0.00378239633202758244,
+                              7.29751555083966205e-5};
+  const double kSqrt32 = 5.656854249492380195206754896838;
+  double xden, xnum, temp, del, xsq;
+  const double eps = DBL_EPSILON * 0.5;
+  const int lower = i_tail != 1, upper = i_tail != 0;
+  const double y = std::fabs(x);
+  *cum = *ccum = 0.0;
+  auto do_del = [&](double X) {
+    xsq = std::trunc(X * 16) / 16;
+    del = (X - xsq) * (X + xsq);
+    if (log_p) {
+      *cum = (-xsq * xsq * 0.5) + (-del * 0.5) + std::log(temp);
+      if ((lower && x > 0.) || (upper && x <= 0.)) *ccum = std::log1p(-std::exp(-xsq * xsq * 0.5) * std::exp(-del * 0.5) * temp);
+    } else {
+      *cum = std::exp(-xsq * xsq * 0.5) * std::exp(-del * 0.5) * temp;
+      *ccum = 1.0 - *cum;
+    }
+  };
+  auto swap_tail = [&]() {
+    if (x > 0.) {
+      temp = *cum;
+      if (lower) *cum = *ccum;
+      *ccum = temp;
+    }
+  };
+  if (y <= 0.67448975) {
+    if (y > eps) {
+      xsq = x * x;
+      xnum = a[4] * xsq;
+      xden = xsq;
+      for (int i = 0; i < 3; ++i) {
+        xnum = (xnum + a[i]) * xsq;
+        xden = (xden + b[i]) * xsq;
+      }
+    } else {
+      xnum = xden = 0.0;
+    }
+    temp = x * (xnum + a[3]) / (xden + b[3]);
+    if (lower) *cum = 0.5 + temp;
+    if (upper) *ccum = 0.5 - temp;
+    if (log_p) {
+      if (lower) *cum = std::log(*cum);
+      if (upper) *ccum = std::log(*ccum);
+    }
+  } else if (y <= kSqrt32) {
+    xnum = c[8] * y;
+    xden = y;
+    for (int i = 0; i < 7; ++i) {
+      xnum = (xnum + c[i]) * y;
+      xden = (xden + d[i]) * y;
+    }
+    temp = (xnum + c[7]) / (xden + d[7]);
+    do_del(y);
+    swap_tail();
+  } else if ((log_p && y < 1e170) || (lower && -37.5193 < x && x < 8.2924) || (upper && -8.2924 < x && x < 37.5193)) {
+    xsq = 1.0 / (x * x);
+    xnum = p[5] * xsq;
+    xden = xsq;
+    for (int i = 0; i < 4; ++i) {
+      xnum = (xnum + p[i]) * xsq;
+      xden = (xden + q[i]) * xsq;
+    }
+    temp = xsq * (xnum + p[4]) / (xden + q[4]);
+    temp = (k1Sqrt2Pi - temp) / y;
+    do_del(x);
+    swap_tail();
+  } else {
+    if (x > 0) { *cum = d1(log_p); *ccum = d0(log_p); }
+    else { *cum = d0(log_p); *ccum = d1(log_p); }
+  }
+}
+
 double pnorm_std(double x, int lower_tail, int log_p) {
-  /* standard normal cdf via erfc (glibc erfc is correctly rounded to < 1 ulp on this range) */
-  double p = lower_tail ? 0.5 * std::erfc(-x * M_SQRT1_2) : 0.5 * std::erfc(x * M_SQRT1_2);
-  return log_p ? std::log(p) : p;
+  if (std::isnan(x)) return x;
+  if (!std::isfinite(x)) return (x < 0) ? (lower_tail ? d0(log_p) : d1(log_p)) : (lower_tail ? d1(log_p) : d0(log_p));
+  double p, cp;
+  pnorm_both(x, &p, &cp, lower_tail ? 0 : 1, log_p);
+  return lower_tail ? p : cp;
 }
 
 double dpnorm(double x, int lower_tail, double lp) {
@@ -359,6 +447,8 @@ double cco_pgamma(double x, double alph, double scale, int lower_tail, int log_p
   if (alph == 0.) return (x <= 0) ? (lower_tail ? d0(log_p) : d1(log_p)) : (lower_tail ? d1(log_p) : d0(log_p));
   return pgamma_raw(x, alph, lower_tail, log_p);
 }
+
+double cco_pnorm(double x, int lower_tail, int log_p) { return pnorm_std(x, lower_tail, log_p); }
 
 double cco_pweibull(double x, double shape, double scale, int lower_tail, int log_p) {
   if (std::isnan(x) || std::isnan(shape) || std::isnan(scale)) return x + shape + scale;

@@ -27,6 +27,7 @@ double cco_dbinom_raw(double x, double n, double p, double q, int give_log);
 double cco_dbinom(double x, double n, double p, int give_log);
 double cco_pgamma(double x, double alph, double scale, int lower_tail, int log_p);
 double cco_pweibull(double x, double shape, double scale, int lower_tail, int log_p);
+double cco_pnorm(double x, int lower_tail, int log_p); /* standard normal, R's pnorm_both (Cody 1969) */
 double cco_dnorm(double x, double mu, double sigma, int give_log);
 double cco_dunif(double x, double a, double b, int give_log);
 double cco_dbeta(double x, double a, double b, int give_log);

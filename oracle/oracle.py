@@ -73,6 +73,8 @@ def lib():
         for name in ("cco_pgamma", "cco_pweibull"):
             getattr(L, name).restype = dbl
             getattr(L, name).argtypes = [dbl] * 3 + [C.c_int, C.c_int]
+        L.cco_pnorm.restype = dbl
+        L.cco_pnorm.argtypes = [dbl, C.c_int, C.c_int]
         L.cco_loglike.restype = dbl
         L.cco_loglike.argtypes = [C.POINTER(_Desc), c_dp, C.c_int, C.POINTER(_Trace)]
         L.cco_logprior.restype = dbl

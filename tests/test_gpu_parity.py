@@ -117,6 +117,35 @@ def test_gamma_table_regimes(built_lib, modfit):
     assert relerr(got, want) <= TOL
 
 
+def test_gamma_table_far_lower_tail_log_space(built_lib, modfit):
+    """sod in (0.001, 0.0055): shapes above 33 500, where gamma-cdf values below 1.002e-292 come out of the Temme-type
+    asymptotic branch and R redoes them in log space through pnorm's log tail (Cody 1969): device = oracle element by element
+    and through the whole likelihood."""
+    from covidcurve_b200 import _lib
+    from oracle.oracle import lib
+    Lo = lib()
+    rng = np.random.default_rng(5)
+    n = 6000
+    a = np.exp(rng.uniform(np.log(33500.0), np.log(1e6), n))
+    z = rng.uniform(-37.5, -34.0, n)                                   # P between 0 (below 1e-324) and ~1e-260
+    x = a + z * np.sqrt(a)
+    want = np.array([Lo.cco_pgamma(xi, ai, 1.0, 1, 0) for xi, ai in zip(x, a)])
+    got = _lib.nmath("pgamma", x, a, 1.0)
+    tiny = want < 1.002e-292
+    assert tiny.sum() > 1500 and (want[tiny] > 0).sum() > 1000
+    assert np.all(np.abs(got - want) <= np.maximum(2 * 4.9406564584124654e-324, 1e-11 * want))
+    spec, g = modfit
+    base = g["theta"][g["loglike"].argmax()].copy()
+    i_sod, i_mod = spec.index("sod"), spec.index("mod")
+    sods = np.geomspace(0.001, 0.0056, 80)
+    mods = np.array([5.0, 12.3, 18.0, 19.8, 33.0, 60.0])
+    th = np.tile(base, (len(sods) * len(mods), 1))
+    th[:, i_sod] = np.tile(sods, len(mods))
+    th[:, i_mod] = np.repeat(mods, len(sods))
+    got, want = _model(spec).loglike(th), _oracle(spec).loglike(th, nthreads=8)
+    assert relerr(got, want) <= TOL
+
+
 def test_device_pointer_path_and_soa_leading_dimension(built_lib, modfit):
     import torch
     from covidcurve_b200 import _lib

@@ -28,6 +28,43 @@ def test_pgamma_against_scipy_and_mpmath():
         assert L.cco_pgamma(x, a, 1.0, 1, 0) == pytest.approx(want, rel=5e-14)
 
 
+def test_pnorm_cody_tables_and_log_tail():
+    """R's pnorm_both (Cody 1969) as restated in the oracle: the coefficient tables are pinned against erfc over the central
+    range and against mpmath in both tails, on the plain and on the log scale (the log tail is what pgamma_raw's log-space
+    redo of the asymptotic branch uses, nmath_port.cpp)."""
+    import math
+    import mpmath as mp
+    L = lib()
+    xs = np.linspace(-8, 8, 4001)
+    ref = np.array([0.5 * math.erfc(-x / math.sqrt(2)) for x in xs])
+    got = _v(lambda x: L.cco_pnorm(x, 1, 0), xs)
+    np.testing.assert_allclose(got, ref, rtol=2e-14)
+    mp.mp.dps = 80
+    for x in (-0.3, 0.5, -0.6744, -0.675, -3.0, 2.0, -5.65, -5.66, -9.0, -20.0, -36.0, -37.4, -37.6, -38.5, -60.0, -500.0, 12.0):
+        for lower in (1, 0):
+            t = x if lower else -x                                     # the requested probability is Phi(t)
+            want = mp.log(mp.ncdf(t)) if t < 0 else mp.log1p(-mp.ncdf(-t))
+            got = L.cco_pnorm(x, lower, 1)
+            assert abs(got - want) <= 4e-15 * max(abs(want), mp.mpf("1e-300")) + 1e-300, (x, lower, got, float(want))
+    # plain scale: R returns exact 0 / 1 beyond its cut-offs (-37.5193, 8.2924)
+    assert L.cco_pnorm(-37.6, 1, 0) == 0.0 and L.cco_pnorm(8.3, 1, 0) == 1.0 and L.cco_pnorm(-37.0, 1, 0) > 0
+    # pgamma far in the lower tail of a very peaked shape: the log-space redo keeps full relative accuracy below 1e-292
+    mp.mp.dps = 60
+    for a, target in ((60000.0, -295), (60000.0, -306), (120000.0, -315), (250000.0, -321), (1e6, -300)):
+        lo_, hi_ = a - 40 * math.sqrt(a), a - 30 * math.sqrt(a)
+        for _ in range(60):                                             # x with P(a, x) = 10^target
+            mid = 0.5 * (lo_ + hi_)
+            if mp.log10(mp.gammainc(a, 0, mid, regularized=True)) < target:
+                lo_ = mid
+            else:
+                hi_ = mid
+        x = float(hi_)
+        want = mp.gammainc(a, 0, x, regularized=True)
+        got = L.cco_pgamma(x, a, 1.0, 1, 0)
+        assert 0 < float(want) < 1.1e-292
+        assert abs(got - want) <= 2e-7 * want + 5e-324, (a, x, got, float(want))   # R's Temme expansion itself is ~1e-8 here
+
+
 def test_dpois_dbinom_against_scipy():
     from scipy import stats
     L = lib()
