@@ -45,6 +45,17 @@ class ModelDesc(C.Structure):
     ]
 
 
+class CallArgs(C.Structure):
+    """cc_call_args: the reference's (params, param_i, data, misc) call shape as plain fields."""
+    _fields_ = [
+        ("n_params", C.c_int32), ("names", C.POINTER(C.c_char_p)),
+        ("obs_deaths", c_dp), ("prop_strata_obs_deaths", c_dp), ("sero_a", c_dp), ("sero_b", c_dp),
+        ("demog", c_dp), ("n_strata", C.c_int32), ("n_knots", C.c_int32), ("rcensor_day", C.c_int32), ("days_obsd", C.c_int32),
+        ("n_sero_obs", C.c_int32), ("sero_survey_start", c_ip), ("sero_survey_end", c_ip),
+        ("max_seroday_obsd", C.c_int32), ("account_serorev", C.c_int32), ("binomial_likelihood", C.c_int32),
+    ]
+
+
 class McmcOpts(C.Structure):
     _fields_ = [
         ("burnin", C.c_int32), ("samples", C.c_int32), ("rungs", C.c_int32), ("n_chains", C.c_int32),
@@ -66,6 +77,7 @@ SYMBOLS = {
     "cc_logprior_batch": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int, _vp]),
     "cc_loglike": (C.c_int, [_vp, c_dp, C.c_int, c_dp]),
     "cc_logprior": (C.c_int, [_vp, c_dp, C.c_int, c_dp]),
+    "cc_loglike_call": (C.c_int, [C.POINTER(CallArgs), c_dp, C.c_int, C.c_int, c_dp]),
     "cc_curves_batch": (C.c_int, [_vp, c_dp, C.c_int64, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
     "cc_mcmc_create": (C.c_int, [_vp, C.POINTER(McmcOpts), C.POINTER(_vp)]),
     "cc_mcmc_advance": (C.c_int, [_vp, C.c_int32]),
@@ -305,6 +317,27 @@ class Mcmc:
         bw = np.empty((P, self.d))
         check(self.L.cc_mcmc_diagnostics(self.h, _dp(beta), _dp(mc), _dp(mv), _dp(bw)))
         return dict(beta=beta, mc_accept=mc, move_accept=mv, bw=bw.reshape(self.chains, self.rungs, self.d))
+
+
+def natcubspline_loglike(params: dict, param_i: int, data: dict, misc: dict, binomial: bool = True, device: int = 0):
+    """COVIDCurve:::natcubspline_loglike_binomial / _logit (R/RcppExports.R:4-10) with the reference's own arguments: `params` a
+    name -> value mapping (an R named vector), `data` and `misc` the lists of R/main.R:136-166.  Returns {"LogLik": value}."""
+    names = [str(k).encode() for k in params]
+    vals = np.ascontiguousarray([float(v) for v in params.values()], dtype=np.float64)
+    f64 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+    i32 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.int32).reshape(-1))
+    keep = dict(names=(C.c_char_p * len(names))(*names), obs=f64(data["obs_deaths"]), prop=f64(data["prop_strata_obs_deaths"]),
+                sa=f64(data["obs_serologypos" if binomial else "obs_serologymu"]), sb=f64(data["obs_serologyn" if binomial else "obs_serologyse"]),
+                demog=f64(misc["demog"]), st=i32(misc["sero_survey_start"]), en=i32(misc["sero_survey_end"]))
+    a = CallArgs(n_params=len(names), names=C.cast(keep["names"], C.POINTER(C.c_char_p)), obs_deaths=_dp(keep["obs"]),
+                 prop_strata_obs_deaths=_dp(keep["prop"]), sero_a=_dp(keep["sa"]), sero_b=_dp(keep["sb"]), demog=_dp(keep["demog"]),
+                 n_strata=keep["demog"].size, n_knots=int(misc["n_knots"]), rcensor_day=int(misc["rcensor_day"]),
+                 days_obsd=int(misc["days_obsd"]), n_sero_obs=int(misc["n_sero_obs"]), sero_survey_start=_ip(keep["st"]),
+                 sero_survey_end=_ip(keep["en"]), max_seroday_obsd=int(misc["max_seroday_obsd"]),
+                 account_serorev=int(bool(misc["account_serorev"])), binomial_likelihood=int(binomial))
+    out = C.c_double()
+    check(load().cc_loglike_call(C.byref(a), _dp(vals), int(param_i), device, C.byref(out)))
+    return {"LogLik": out.value}
 
 
 FN = dict(pgamma=1, dpois=2, dbinom=3, dnorm=4, dbeta=5, dunif=6, pweibull=7, stirlerr=8, bd0=9, fastlog=10, rpois=11)

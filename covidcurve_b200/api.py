@@ -268,11 +268,13 @@ def _checks(IFRmodel, binomial_likelihood, reparamIFR, reparamInfxn, reparamKnot
 def run_IFRmodel_age(IFRmodel, binomial_likelihood=True, reparamIFR=True, reparamInfxn=True, reparamKnots=True, thinning=0,
                      burnin=1000, samples=10000, rungs=1, chains=5, coupling_on=True, GTI_pow=1.0, beta_manual=None, cluster=None,
                      pb_markdown=False, silent=False, *, seed: int = 1, device: int = 0, record_all_rungs: bool = True,
-                     cold_rung_last: bool = True, chain_offset: int = 0):
+                     cold_rung_last: bool = False, chain_offset: int = 0):
     """Run the age-stratified IFR model (R/main.R:12).  Same arguments as the reference; `cluster`, `pb_markdown` and
     `silent` are accepted and ignored (chains run concurrently on the GPU, there is no progress bar).  Keyword-only
-    extras: RNG `seed`, CUDA `device`, `record_all_rungs` (drjacoby records every rung), `cold_rung_last`,
-    `chain_offset` (global id of the first chain when a run is sharded over several processes / GPUs).
+    extras: RNG `seed`, CUDA `device`, `record_all_rungs` (drjacoby records every rung), `cold_rung_last` (default False:
+    "rung1" is the cold chain, the label every consumer in R/summarize_plot.R:68,164,276,591,687 reads; `rung_details` states
+    the thermodynamic power of every label), `chain_offset` (global id of the first chain when a run is sharded over several
+    processes / GPUs).
 
     Returns an `IFRmodel_inf`-shaped dict: {"inputs": {...}, "mcmcout": {"output", "diagnostics", "parameters"}}.
     """
@@ -327,7 +329,8 @@ def assemble_drjacoby_output(spec, draws, diag, burnin, samples, rungs, chains, 
     """
     theta, ll, lp, it = draws["theta"], draws["loglike"], draws["logprior"], draws["iteration"]
     C_, Rr, rows, d = theta.shape
-    cold_pos = (rungs - 1) if cold_rung_last else 0
+    # the cold chain is wherever the ladder says it is (beta_manual overrides the orientation flag on the C side)
+    cold_pos = int(np.argmax(diag["beta"])) if len(np.atleast_1d(diag["beta"])) == rungs else ((rungs - 1) if cold_rung_last else 0)
     rung_ids = np.arange(1, rungs + 1) if record_all_rungs else np.array([cold_pos + 1])
     chain_col = np.repeat(np.array(["chain%d" % (chain_offset + c + 1) for c in range(C_)]), Rr * rows)
     rung_col = np.tile(np.repeat(np.array(["rung%d" % r for r in rung_ids]), rows), C_)
@@ -341,7 +344,7 @@ def assemble_drjacoby_output(spec, draws, diag, burnin, samples, rungs, chains, 
     output = pd.DataFrame(cols)
     rhat = None
     if rhat_fn is not None and chains > 1 and samples > 1:
-        q = (Rr - 1 if cold_rung_last else 0) if record_all_rungs else 0
+        q = cold_pos if record_all_rungs else 0
         samp = it > burnin
         rhat = rhat_fn(theta[:, q][:, samp, :])
         rhat = pd.Series(rhat, index=spec.names)

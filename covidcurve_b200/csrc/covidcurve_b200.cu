@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -1305,6 +1306,96 @@ extern "C" int cc_loglike(cc_model* m, const double* params, int /*param_i: igno
 
 extern "C" int cc_logprior(cc_model* m, const double* params, int /*param_i*/, double* out) {
   return batch_call(m, launch_logprior, params, 1, 1, out, CC_MEM_HOST, nullptr, "cc_logprior");
+}
+
+// ---- the reference's 4-argument call shape (header: cc_call_args): role map from the names, model handles cached by content
+namespace {
+struct CallCacheEntry { uint64_t key = 0; int device = -1; cc_model* model = nullptr; uint64_t stamp = 0; };
+std::mutex g_call_mu;
+CallCacheEntry g_call_cache[4];
+uint64_t g_call_stamp = 0;
+
+uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+  return h;
+}
+int find_name(const cc_call_args* a, const std::string& nm) {
+  for (int i = 0; i < a->n_params; i++)
+    if (a->names[i] && nm == a->names[i]) return i;
+  return -1;
+}
+}  // namespace
+
+extern "C" int cc_loglike_call(const cc_call_args* a, const double* params, int param_i, int device, double* out) {
+  if (!a || !params || !out) return fail(CC_E_INVALID, "cc_loglike_call: null argument");
+  if (!a->names || !a->obs_deaths || !a->prop_strata_obs_deaths || !a->sero_a || !a->sero_b || !a->demog || !a->sero_survey_start ||
+      !a->sero_survey_end)
+    return fail(CC_E_INVALID, "cc_loglike_call: null field in cc_call_args");
+  const int d = a->n_params, A = a->n_strata, K = a->n_knots, T = a->days_obsd, S = a->n_sero_obs;
+  if (d < 1 || d > CC_MAX_PARAMS || A < 1 || A > CC_MAX_STRATA || K < 3 || K > CC_MAX_KNOTS || T < 1 || T > CC_MAX_DAYS || S < 1 ||
+      S > CC_MAX_SEROSURVEYS)
+    return fail(CC_E_INVALID, "cc_loglike_call: sizes out of range");
+  uint64_t h = 1469598103934665603ULL;
+  for (int i = 0; i < d; i++) {
+    if (!a->names[i]) return fail(CC_E_INVALID, "cc_loglike_call: params must be a fully named vector");
+    h = fnv1a(h, a->names[i], std::strlen(a->names[i]) + 1);
+  }
+  const int32_t scal[9] = {d, A, K, a->rcensor_day, T, S, a->max_seroday_obsd, a->account_serorev, a->binomial_likelihood};
+  h = fnv1a(h, scal, sizeof scal);
+  h = fnv1a(h, a->obs_deaths, sizeof(double) * T);
+  h = fnv1a(h, a->prop_strata_obs_deaths, sizeof(double) * A);
+  h = fnv1a(h, a->sero_a, sizeof(double) * S * A);
+  h = fnv1a(h, a->sero_b, sizeof(double) * S * A);
+  h = fnv1a(h, a->demog, sizeof(double) * A);
+  h = fnv1a(h, a->sero_survey_start, sizeof(int32_t) * S);
+  h = fnv1a(h, a->sero_survey_end, sizeof(int32_t) * S);
+
+  std::lock_guard<std::mutex> lock(g_call_mu);
+  cc_model* m = nullptr;
+  for (auto& e : g_call_cache)
+    if (e.model && e.key == h && e.device == device) { m = e.model; e.stamp = ++g_call_stamp; }
+  if (!m) {
+    // role map by name (binomial.cpp:21-55; generated form Agecpp2strings.R:255-368)
+    auto need = [&](const std::string& nm, int* row) {
+      *row = find_name(a, nm);
+      return *row >= 0;
+    };
+    cc_model_desc de;
+    std::memset(&de, 0, sizeof de);
+    de.abi_version = CC_ABI_VERSION;
+    de.n_params = d; de.n_strata = A; de.n_knots = K; de.days_obsd = T; de.n_sero_obs = S;
+    de.max_seroday_obsd = a->max_seroday_obsd; de.rcensor_day = a->rcensor_day; de.account_serorev = a->account_serorev ? 1 : 0;
+    de.binomial_likelihood = a->binomial_likelihood ? 1 : 0;
+    de.demog = a->demog; de.obs_deaths = a->obs_deaths; de.prop_strata_obs_deaths = a->prop_strata_obs_deaths;
+    de.sero_a = a->sero_a; de.sero_b = a->sero_b; de.sero_survey_start = a->sero_survey_start; de.sero_survey_end = a->sero_survey_end;
+    std::string missing;
+    auto want = [&](const std::string& nm, int32_t* row) { int r; if (!need(nm, &r)) { if (missing.empty()) missing = nm; r = 0; } *row = r; };
+    want("sens", &de.idx_sens); want("spec", &de.idx_spec); want("sero_con_rate", &de.idx_sero_con_rate);
+    want("mod", &de.idx_mod); want("sod", &de.idx_sod);
+    de.idx_sero_rev_shape = de.idx_sero_rev_scale = -1;
+    if (a->account_serorev) { want("sero_rev_shape", &de.idx_sero_rev_shape); want("sero_rev_scale", &de.idx_sero_rev_scale); }
+    std::vector<int32_t> knots(K - 1), infxn(K), ifr(A), noise(A);
+    for (int i = 0; i < K - 1; i++) want("x" + std::to_string(i + 1), &knots[i]);
+    for (int i = 0; i < K; i++) want("y" + std::to_string(i + 1), &infxn[i]);
+    for (int i = 0; i < A; i++) want("ma" + std::to_string(i + 1), &ifr[i]);
+    for (int i = 0; i < A; i++) want("ne" + std::to_string(i + 1), &noise[i]);
+    if (!missing.empty()) return fail(CC_E_INVALID, "cc_loglike_call: params has no element named '" + missing + "'");
+    de.idx_knots = knots.data(); de.idx_infxn = infxn.data(); de.idx_ifr = ifr.data(); de.idx_noise = noise.data();
+    de.idx_rel_knot = de.idx_rel_infxn = de.idx_max_ma = -1;
+    std::vector<double> lo(d, -INFINITY), hi(d, INFINITY), zero(d, 0.0);
+    std::vector<int32_t> fam(d, CC_PRIOR_NONE);
+    de.pmin = lo.data(); de.pmax = hi.data(); de.prior_family = fam.data(); de.prior_p1 = zero.data(); de.prior_p2 = zero.data();
+    de.jac_rows[0] = de.jac_rows[1] = de.jac_rows[2] = -1;
+    int rc = cc_model_create(&de, device, &m);
+    if (rc) return rc;
+    CallCacheEntry* victim = &g_call_cache[0];
+    for (auto& e : g_call_cache)
+      if (!e.model) { victim = &e; break; } else if (e.stamp < victim->stamp) victim = &e;
+    if (victim->model) cc_model_destroy(victim->model);
+    victim->key = h; victim->device = device; victim->model = m; victim->stamp = ++g_call_stamp;
+  }
+  return cc_loglike(m, params, param_i, out);
 }
 
 extern "C" int cc_last_kernel_ms(cc_model* m, double* ms, int32_t* launches) {

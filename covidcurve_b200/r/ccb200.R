@@ -57,13 +57,18 @@ ccb200_descriptor <- function(IFRmodel, data_list, misc_list, binomial_likelihoo
 
 ccb200_run_mcmc <- function(IFRmodel, data_list, misc_list, df_params, binomial_likelihood, account_serorev,
                             reparamIFR, reparamInfxn, reparamKnots, burnin, samples, chains, rungs,
-                            coupling_on, GTI_pow, beta_manual, seed = sample.int(.Machine$integer.max, 1), device = 0L) {
+                            coupling_on, GTI_pow, beta_manual, seed = sample.int(.Machine$integer.max, 1), device = 0L,
+                            cold_rung_last = FALSE, thin = 1L) {
+  # Rung labels: every consumer in COVIDCurve reads the posterior from "rung1" (R/summarize_plot.R:68,164,276,591,687), so by
+  # default rung1 is the cold chain (thermodynamic power 1) and the powers descend to 0 at the last rung; rung_details states
+  # the power of every label either way.
   desc <- ccb200_descriptor(IFRmodel, data_list, misc_list, binomial_likelihood, account_serorev, reparamIFR, reparamInfxn, reparamKnots)
   model <- .Call("CCB_model_create", desc, as.integer(device), PACKAGE = "ccb200")
   res <- .Call("CCB_mcmc_run", model,
                list(burnin = as.integer(burnin), samples = as.integer(samples), rungs = as.integer(rungs), chains = as.integer(chains),
                     coupling_on = as.integer(coupling_on), GTI_pow = as.numeric(GTI_pow), beta_manual = beta_manual,
-                    seed = as.numeric(seed), init = as.numeric(df_params$init)), PACKAGE = "ccb200")
+                    seed = as.numeric(seed), init = as.numeric(df_params$init), cold_rung_last = as.integer(cold_rung_last),
+                    thin = as.integer(thin)), PACKAGE = "ccb200")
   d <- nrow(df_params); rows <- length(res$iteration)
   theta <- array(res$theta, dim = c(d, rows, rungs, chains))
   grid <- expand.grid(iteration = res$iteration, rung = seq_len(rungs), chain = seq_len(chains))
@@ -72,7 +77,7 @@ ccb200_run_mcmc <- function(IFRmodel, data_list, misc_list, df_params, binomial_
                        logprior = as.numeric(res$logprior), loglikelihood = as.numeric(res$loglikelihood), stringsAsFactors = FALSE)
   pars <- matrix(aperm(theta, c(2, 3, 4, 1)), ncol = d, dimnames = list(NULL, df_params$name))
   output <- cbind(output, as.data.frame(pars))
-  cold <- output[output$rung == paste0("rung", rungs) & output$stage == "sampling", ]
+  cold <- output[output$rung == paste0("rung", which.max(res$beta)) & output$stage == "sampling", ]
   rhat <- if (chains > 1) vapply(df_params$name, function(p) {
     x <- matrix(cold[[p]], ncol = chains); n <- nrow(x)
     W <- mean(apply(x, 2, stats::var)); B <- n * stats::var(colMeans(x)); sqrt(((1 - 1 / n) * W + B / n) / W) }, numeric(1)) else NULL

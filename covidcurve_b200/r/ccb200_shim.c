@@ -1,9 +1,10 @@
 /*
  * ccb200_shim.c - the .Call layer an R installation of COVIDCurve adds to reach libcovidcurve_b200.so.
  *
- * NOT compiled in this repository's build (R and its headers are absent from the build image):
- * it is the thin binding a maintainer drops into COVIDCurve/src/ next to RcppExports.cpp.  Every entry point only
- * unpacks R vectors into the plain-pointer C ABI of include/covidcurve_b200.h; no logic lives here.
+ * R and its headers are absent from this repository's build image, so the file is not linked here; it is
+ * type-checked against minimal declarations of the R API (tests/r_stubs/, tests/test_abi.py::test_r_shim_compiles).  It is the
+ * thin binding a maintainer drops into COVIDCurve/src/ next to RcppExports.cpp.  Every entry point only unpacks R vectors
+ * into the plain-pointer C ABI of include/covidcurve_b200.h; no logic lives here.
  *
  * Replaces, on the R side:
  *   .Call("_COVIDCurve_natcubspline_loglike_binomial" | "..._logit", params, param_i, data, misc)   src/RcppExports.cpp:10-35
@@ -28,7 +29,18 @@ static SEXP list_get(SEXP lst, const char* name) {
   Rf_error("missing element '%s'", name);
   return R_NilValue;
 }
+static SEXP list_get_opt(SEXP lst, const char* name) { /* R_NilValue when absent */
+  SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  if (Rf_isNull(names)) return R_NilValue;
+  for (R_xlen_t i = 0; i < XLENGTH(lst); i++)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(lst, i);
+  return R_NilValue;
+}
 static int as_int(SEXP x) { return Rf_asInteger(x); }
+static int opt_int(SEXP lst, const char* name, int dflt) {
+  SEXP v = list_get_opt(lst, name);
+  return Rf_isNull(v) ? dflt : Rf_asInteger(v);
+}
 
 static void model_finalizer(SEXP ptr) {
   cc_model* m = (cc_model*)R_ExternalPtrAddr(ptr);
@@ -96,7 +108,7 @@ SEXP CCB_model_create(SEXP desc, SEXP device) {
   return ptr;
 }
 
-/* scalar drop-ins for COVIDCurve:::natcubspline_loglike_binomial/_logit (R/RcppExports.R:4-10): list(LogLik = ) */
+/* scalar evaluation on an existing model handle: list(LogLik = ) like R/RcppExports.R:4-10 */
 SEXP CCB_loglike(SEXP model, SEXP params, SEXP param_i) {
   cc_model* m = (cc_model*)R_ExternalPtrAddr(model);
   double out = NA_REAL;
@@ -107,6 +119,76 @@ SEXP CCB_loglike(SEXP model, SEXP params, SEXP param_i) {
   Rf_setAttrib(ret, R_NamesSymbol, nm);
   UNPROTECT(2);
   return ret;
+}
+
+/*
+ * The reference's own 4-argument call shape, (params, param_i, data, misc) - src/RcppExports.cpp:10-35, R/RcppExports.R:4-10,
+ * and the signature of the drjacoby loglike slot (R/Agecpp2strings.R:389): a NAMED numeric vector plus the data and misc
+ * lists of R/main.R:136-166.  tests/testthat/test-check_natcub_cpp.R:114-150 binds to these unchanged.  `binomial` < 0:
+ * decide from the data list (obs_serologypos present -> binomial, else logit-normal).
+ */
+static double call_shape_loglike(SEXP params, SEXP param_i, SEXP data, SEXP misc, int binomial) {
+  SEXP names = Rf_getAttrib(params, R_NamesSymbol);
+  if (Rf_isNull(names)) Rf_error("params must be a named numeric vector");
+  const int d = Rf_length(params);
+  const char** nm = (const char**)R_alloc((size_t)d, sizeof(const char*));
+  for (int i = 0; i < d; i++) nm[i] = CHAR(STRING_ELT(names, i));
+  if (binomial < 0) binomial = Rf_isNull(list_get_opt(data, "obs_serologypos")) ? 0 : 1;
+  int np = 0;
+  SEXP p_par = PROTECT(Rf_coerceVector(params, REALSXP)); np++;
+  SEXP obs = PROTECT(Rf_coerceVector(list_get(data, "obs_deaths"), REALSXP)); np++;
+  SEXP prop = PROTECT(Rf_coerceVector(list_get(data, "prop_strata_obs_deaths"), REALSXP)); np++;
+  SEXP sa = PROTECT(Rf_coerceVector(list_get(data, binomial ? "obs_serologypos" : "obs_serologymu"), REALSXP)); np++;
+  SEXP sb = PROTECT(Rf_coerceVector(list_get(data, binomial ? "obs_serologyn" : "obs_serologyse"), REALSXP)); np++;
+  SEXP demog = PROTECT(Rf_coerceVector(list_get(misc, "demog"), REALSXP)); np++;
+  SEXP st = PROTECT(Rf_coerceVector(list_get(misc, "sero_survey_start"), INTSXP)); np++;
+  SEXP en = PROTECT(Rf_coerceVector(list_get(misc, "sero_survey_end"), INTSXP)); np++;
+  cc_call_args a;
+  memset(&a, 0, sizeof a);
+  a.n_params = d;
+  a.names = nm;
+  a.obs_deaths = REAL(obs);
+  a.prop_strata_obs_deaths = REAL(prop);
+  a.sero_a = REAL(sa);
+  a.sero_b = REAL(sb);
+  a.demog = REAL(demog);
+  a.n_strata = Rf_length(demog);
+  a.n_knots = as_int(list_get(misc, "n_knots"));
+  a.rcensor_day = as_int(list_get(misc, "rcensor_day"));
+  a.days_obsd = as_int(list_get(misc, "days_obsd"));
+  a.n_sero_obs = as_int(list_get(misc, "n_sero_obs"));
+  a.sero_survey_start = INTEGER(st);
+  a.sero_survey_end = INTEGER(en);
+  a.max_seroday_obsd = as_int(list_get(misc, "max_seroday_obsd"));
+  a.account_serorev = Rf_asLogical(list_get(misc, "account_serorev")) == TRUE;
+  a.binomial_likelihood = binomial;
+  if (Rf_length(obs) != a.days_obsd || Rf_length(prop) != a.n_strata || Rf_length(sa) != a.n_sero_obs * a.n_strata ||
+      Rf_length(sb) != a.n_sero_obs * a.n_strata || Rf_length(st) != a.n_sero_obs || Rf_length(en) != a.n_sero_obs)
+    Rf_error("data / misc vectors do not have the lengths misc announces");
+  double out = NA_REAL;
+  const int rc = cc_loglike_call(&a, REAL(p_par), as_int(param_i), opt_int(misc, "ccb200_device", 0), &out);
+  UNPROTECT(np);
+  if (rc != CC_OK) ccb_fail("cc_loglike_call");
+  return out;
+}
+static SEXP loglik_list(double v) {
+  SEXP ret = PROTECT(Rf_allocVector(VECSXP, 1)), nm = PROTECT(Rf_allocVector(STRSXP, 1));
+  SET_VECTOR_ELT(ret, 0, Rf_ScalarReal(v));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("LogLik"));
+  Rf_setAttrib(ret, R_NamesSymbol, nm);
+  UNPROTECT(2);
+  return ret;
+}
+/* drop-in replacements of the two registered twins: same symbol names, same arity, same return value list(LogLik = ) */
+SEXP _COVIDCurve_natcubspline_loglike_binomial(SEXP params, SEXP param_i, SEXP data, SEXP misc) {
+  return loglik_list(call_shape_loglike(params, param_i, data, misc, 1));
+}
+SEXP _COVIDCurve_natcubspline_loglike_logit(SEXP params, SEXP param_i, SEXP data, SEXP misc) {
+  return loglik_list(call_shape_loglike(params, param_i, data, misc, 0));
+}
+/* the drjacoby user-function shape: SEXP loglike(params, param_i, data, misc) returning a double (Agecpp2strings.R:389-401) */
+SEXP CC_loglike(SEXP params, SEXP param_i, SEXP data, SEXP misc) {
+  return Rf_ScalarReal(call_shape_loglike(params, param_i, data, misc, -1));
 }
 
 /* batched evaluation: theta is an n x d numeric matrix (one parameter vector per ROW, columns in df_params order); R's
@@ -148,18 +230,24 @@ SEXP CCB_mcmc_run(SEXP model, SEXP opts) {
   SEXP bm = list_get(opts, "beta_manual");
   o.beta_manual = Rf_isNull(bm) ? NULL : REAL(bm);
   o.seed = (uint64_t)Rf_asReal(list_get(opts, "seed"));
-  o.cold_rung_last = 1;
-  o.record_rungs = 1;
-  o.thin = 1;
+  /* rung orientation: every consumer in COVIDCurve reads the posterior from "rung1" (R/summarize_plot.R:68,164,276,591,687;
+     vignettes/runningmodel.Rmd:238-299), so by default rung 1 is the cold chain (beta = 1) and the powers descend to 0 at
+     rung `rungs`; opts$cold_rung_last = TRUE gives the ascending ladder instead.  rung_details (returned `beta`) always
+     states which power each rung label carries. */
+  o.cold_rung_last = opt_int(opts, "cold_rung_last", 0);
+  o.record_rungs = opt_int(opts, "record_rungs", 1);
+  o.thin = opt_int(opts, "thin", 1);
+  o.bw_per_particle = opt_int(opts, "bw_per_particle", 0);
+  o.no_adapt_in_sampling = opt_int(opts, "no_adapt_in_sampling", 0);
   o.init = NULL;
   o.init_default = REAL(list_get(opts, "init"));
   cc_mcmc* s = NULL;
   if (cc_mcmc_create(m, &o, &s) != CC_OK) ccb_fail("cc_mcmc_create");
   if (cc_mcmc_advance(s, o.burnin + o.samples - 1) != CC_OK) { cc_mcmc_destroy(s); ccb_fail("cc_mcmc_advance"); }
-  const R_xlen_t rows = (R_xlen_t)cc_mcmc_rows(s), d = Rf_length(list_get(opts, "init")), R = o.rungs, C = o.n_chains;
+  const R_xlen_t rows = (R_xlen_t)cc_mcmc_rows(s), d = Rf_length(list_get(opts, "init")), R = o.record_rungs ? o.rungs : 1, C = o.n_chains;
   SEXP theta = PROTECT(Rf_allocVector(REALSXP, rows * d * R * C)), ll = PROTECT(Rf_allocVector(REALSXP, rows * R * C)),
        lp = PROTECT(Rf_allocVector(REALSXP, rows * R * C)), it = PROTECT(Rf_allocVector(INTSXP, rows)),
-       beta = PROTECT(Rf_allocVector(REALSXP, R)), acc = PROTECT(Rf_allocVector(REALSXP, (R > 1 ? R - 1 : 1) * C));
+       beta = PROTECT(Rf_allocVector(REALSXP, o.rungs)), acc = PROTECT(Rf_allocVector(REALSXP, (o.rungs > 1 ? o.rungs - 1 : 1) * C));
   /* the C layout [chain][rung][row][d] read as column-major is a d x rows x rungs x chains array */
   if (cc_mcmc_fetch(s, REAL(theta), REAL(ll), REAL(lp), INTEGER(it)) != CC_OK ||
       cc_mcmc_diagnostics(s, REAL(beta), REAL(acc), NULL, NULL) != CC_OK) {
@@ -180,9 +268,16 @@ SEXP CCB_mcmc_run(SEXP model, SEXP opts) {
 }
 
 static const R_CallMethodDef CallEntries[] = {
-    {"CCB_model_create", (DL_FUNC)&CCB_model_create, 2},   {"CCB_loglike", (DL_FUNC)&CCB_loglike, 3},
-    {"CCB_loglike_batch", (DL_FUNC)&CCB_loglike_batch, 2}, {"CCB_logprior_batch", (DL_FUNC)&CCB_logprior_batch, 2},
-    {"CCB_mcmc_run", (DL_FUNC)&CCB_mcmc_run, 2},           {NULL, NULL, 0}};
+    {"CCB_model_create", (DL_FUNC)&CCB_model_create, 2},
+    {"CCB_loglike", (DL_FUNC)&CCB_loglike, 3},
+    {"CCB_loglike_batch", (DL_FUNC)&CCB_loglike_batch, 2},
+    {"CCB_logprior_batch", (DL_FUNC)&CCB_logprior_batch, 2},
+    {"CCB_mcmc_run", (DL_FUNC)&CCB_mcmc_run, 2},
+    /* the reference's own registration table (src/RcppExports.cpp:37-41): same names, same arity */
+    {"_COVIDCurve_natcubspline_loglike_binomial", (DL_FUNC)&_COVIDCurve_natcubspline_loglike_binomial, 4},
+    {"_COVIDCurve_natcubspline_loglike_logit", (DL_FUNC)&_COVIDCurve_natcubspline_loglike_logit, 4},
+    {"CC_loglike", (DL_FUNC)&CC_loglike, 4},
+    {NULL, NULL, 0}};
 
 void R_init_ccb200(DllInfo* dll) {
   R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);

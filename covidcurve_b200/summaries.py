@@ -127,10 +127,13 @@ def effective_size(x: np.ndarray) -> float:
 
 
 def geweke_z(x: np.ndarray, frac1: float = 0.1, frac2: float = 0.5) -> float:
-    """coda::geweke.diag z-score for one series."""
+    """coda::geweke.diag z-score for one series.  Windows as coda takes them (1-based, inclusive):
+    first 1 .. ceiling(1 + frac1 (n - 1)), second floor(n - frac2 (n - 1)) .. n  (n = 10 000: 1 001 and 5 001 points)."""
     x = np.asarray(x, dtype=np.float64)
     n = x.size
-    a, b = x[: max(int(np.floor(frac1 * (n - 1))) + 1, 1)], x[n - max(int(np.floor(frac2 * (n - 1))) + 1, 1):]
+    end1 = int(np.ceil(1 + frac1 * (n - 1)))
+    start2 = int(np.floor(n - frac2 * (n - 1)))
+    a, b = x[:max(end1, 1)], x[max(start2, 1) - 1:]
     va, vb = _spectrum0_ar(a) / a.size, _spectrum0_ar(b) / b.size
     with np.errstate(divide="ignore", invalid="ignore"):
         return float((a.mean() - b.mean()) / np.sqrt(va + vb))
@@ -151,11 +154,12 @@ def default_cold_rung(modout) -> str:
 
 def get_cred_intervals(IFRmodel_inf, what: str, whichrung: str | None = None, by_chain: bool = True) -> pd.DataFrame:
     """R/summarize_plot.R:68-153.  what in {"IFRparams", "Knotparams", "Infxnparams", "Serotestparams", "Noiseparams",
-    "TODparams"}: per (chain?, param) min, LCI (2.5 %), median, mean, UCI (97.5 %), max, ESS, Geweke z and its density."""
+    "DeathDelayparams"}: per (chain?, param) min, LCI (2.5 %), median, mean, UCI (97.5 %), max, ESS, Geweke z and its density."""
     from scipy import stats
     m = IFRmodel_inf["inputs"]["IFRmodel"]
     groups = dict(IFRparams=m.IFRparams, Knotparams=m.Knotparams, Infxnparams=m.Infxnparams, Serotestparams=m.Serotestparams,
-                  Noiseparams=m.Noiseparams or [], TODparams=[m.modparam, m.sodparam])
+                  Noiseparams=m.Noiseparams or [], DeathDelayparams=[m.modparam, m.sodparam])   # summarize_plot.R:72,124
+    groups["TODparams"] = groups["DeathDelayparams"]                                            # alias kept from round 1
     if what not in groups:
         raise ValueError("what must be one of %s" % list(groups))
     rung = whichrung or default_cold_rung(IFRmodel_inf)

@@ -136,6 +136,34 @@ int cc_loglike(cc_model* m, const double* params, int param_i, double* out);
 int cc_logprior(cc_model* m, const double* params, int param_i, double* out);
 
 /*
+ * The reference's own call shape, for the static twins
+ *     .Call("_COVIDCurve_natcubspline_loglike_binomial" | "..._logit", params, param_i, data, misc)   src/RcppExports.cpp:10-35
+ * which COVIDCurve's unit test drives directly (tests/testthat/test-check_natcub_cpp.R:114-150): a NAMED parameter vector plus
+ * the data and misc lists, no model handle.  `cc_call_args` is those two lists and names(params) as plain fields; the role map
+ * is the twins' fixed naming (binomial.cpp:21-55, generalised in A and K like the generator, Agecpp2strings.R:255-368):
+ * sens, spec, sero_con_rate, sero_rev_shape, sero_rev_scale (read only when account_serorev), mod, sod, x1..x{K-1}, y1..yK,
+ * ma1..maA, ne1..neA.  The library keeps the model handles of the most recent distinct (names, data, misc) triples, so a
+ * repeated call costs one batch-of-one evaluation.  A name that is missing is an error (Rcpp's params["name"] throws).
+ */
+typedef struct cc_call_args {
+  int32_t n_params;
+  const char* const* names;             /* [n_params] names(params) */
+  /* data (R/main.R:136-152) */
+  const double* obs_deaths;             /* [days_obsd] */
+  const double* prop_strata_obs_deaths; /* [n_strata] */
+  const double* sero_a;                 /* [n_sero_obs * n_strata] obs_serologypos | obs_serologymu */
+  const double* sero_b;                 /* [n_sero_obs * n_strata] obs_serologyn   | obs_serologyse */
+  /* misc (R/main.R:158-166) */
+  const double* demog;                  /* [n_strata] */
+  int32_t n_strata, n_knots, rcensor_day, days_obsd, n_sero_obs;
+  const int32_t* sero_survey_start;     /* [n_sero_obs] */
+  const int32_t* sero_survey_end;       /* [n_sero_obs] */
+  int32_t max_seroday_obsd, account_serorev;
+  int32_t binomial_likelihood;          /* 1: natcubspline_loglike_binomial, 0: natcubspline_loglike_logit */
+} cc_call_args;
+int cc_loglike_call(const cc_call_args* args, const double* params, int param_i, int device, double* out);
+
+/*
  * Intermediates of one evaluation, for the post-processing re-entry points (R/summarize_plot.R:276-884):
  * any output pointer may be NULL.  Host pointers.  Batched over n parameter vectors (SoA like above).
  *   infxn    [n][T]   exp(spline) incidence                 (draw_posterior_infxn_cubic_splines, per stratum = ne[a]*infxn)

@@ -1,0 +1,62 @@
+/* Minimal stand-in for R's <Rinternals.h> (see R.h in this directory): the SEXP API the shim uses, declarations only. */
+#ifndef CCB_STUB_RINTERNALS_H
+#define CCB_STUB_RINTERNALS_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct SEXPREC* SEXP;
+typedef ptrdiff_t R_xlen_t;
+typedef unsigned int SEXPTYPE;
+typedef enum { FALSE = 0, TRUE } Rboolean;
+#define NILSXP 0
+#define LGLSXP 10
+#define INTSXP 13
+#define REALSXP 14
+#define STRSXP 16
+#define VECSXP 19
+extern SEXP R_NilValue, R_NamesSymbol, R_NaString;
+extern double R_NaReal;
+extern int R_NaInt;
+#define NA_REAL R_NaReal
+#define NA_INTEGER R_NaInt
+#define NA_STRING R_NaString
+double* REAL(SEXP x);
+int* INTEGER(SEXP x);
+int* LOGICAL(SEXP x);
+const char* CHAR(SEXP x);
+SEXP STRING_ELT(SEXP x, R_xlen_t i);
+SEXP VECTOR_ELT(SEXP x, R_xlen_t i);
+SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
+void SET_STRING_ELT(SEXP x, R_xlen_t i, SEXP v);
+R_xlen_t XLENGTH(SEXP x);
+int Rf_length(SEXP x);
+int Rf_nrows(SEXP x);
+int Rf_ncols(SEXP x);
+int TYPEOF(SEXP x);
+SEXP Rf_getAttrib(SEXP x, SEXP name);
+SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP val);
+SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n);
+SEXP Rf_coerceVector(SEXP x, SEXPTYPE type);
+SEXP Rf_mkChar(const char* s);
+SEXP Rf_ScalarReal(double x);
+SEXP Rf_ScalarInteger(int x);
+int Rf_asInteger(SEXP x);
+int Rf_asLogical(SEXP x);
+double Rf_asReal(SEXP x);
+Rboolean Rf_isNull(SEXP x);
+Rboolean Rf_isReal(SEXP x);
+Rboolean Rf_isInteger(SEXP x);
+SEXP Rf_protect(SEXP x);
+void Rf_unprotect(int n);
+#define PROTECT(x) Rf_protect(x)
+#define UNPROTECT(n) Rf_unprotect(n)
+SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot);
+void* R_ExternalPtrAddr(SEXP s);
+void R_ClearExternalPtr(SEXP s);
+typedef void (*R_CFinalizer_t)(SEXP);
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -26,7 +26,7 @@ def test_struct_layouts_match_header():
     from covidcurve_b200 import _lib
     src = open(os.path.join(ROOT, "include", "covidcurve_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    for cname, cls in (("cc_model_desc", _lib.ModelDesc), ("cc_mcmc_opts", _lib.McmcOpts)):
+    for cname, cls in (("cc_model_desc", _lib.ModelDesc), ("cc_mcmc_opts", _lib.McmcOpts), ("cc_call_args", _lib.CallArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
         fields = []
         for decl in body.split(";"):
@@ -34,6 +34,7 @@ def test_struct_layouts_match_header():
             if not decl:
                 continue
             names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split(None, 2)[2]
+            names = re.sub(r"^(char\s*\*\s*)?const\s*\*", "", names.strip())          # `const char* const* names`
             for n in names.split(","):
                 fields.append(re.sub(r"[\*\s]|\[.*?\]", "", n))
         assert fields == [f[0] for f in cls._fields_], cname
@@ -61,3 +62,18 @@ def test_product_path_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "libcc_oracle" not in txt and "cc_oracle.h" not in txt and "nmath_port" not in txt, f
+
+
+def test_r_shim_compiles():
+    """The R .Call layer (covidcurve_b200/r/ccb200_shim.c) type-checks against the C ABI header and the R API declarations in
+    tests/r_stubs/ (R itself is absent from the build image), and registers the reference's own entry points with their arity
+    (src/RcppExports.cpp:37-41)."""
+    import subprocess
+    shim = os.path.join(ROOT, "covidcurve_b200", "r", "ccb200_shim.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-I", os.path.join(ROOT, "tests", "r_stubs"),
+                        "-I", os.path.join(ROOT, "include"), shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(shim).read()
+    for sym in ("_COVIDCurve_natcubspline_loglike_binomial", "_COVIDCurve_natcubspline_loglike_logit", "CC_loglike"):
+        assert re.search(r'\{"%s", \(DL_FUNC\)&%s, 4\}' % (sym, sym), src), sym
+    assert "cold_rung_last" in src and 'opt_int(opts, "thin", 1)' in src

@@ -102,6 +102,18 @@ def test_gelman_rubin_and_ess_on_known_series():
     assert abs(summaries.geweke_z(iid[1, :, 1])) < 4
 
 
+def test_geweke_windows_are_codas(monkeypatch):
+    """coda::geweke.diag: first window 1..ceiling(1 + 0.1 (n-1)), second floor(n - 0.5 (n-1))..n - 1 001 and 5 001 points for
+    n = 10 000 (what get_cred_intervals' GewekeZ is computed on, R/summarize_plot.R:150)."""
+    seen = []
+    monkeypatch.setattr(summaries, "_spectrum0_ar", lambda w: (seen.append((w[0], w[-1], w.size)), 1.0)[1])
+    summaries.geweke_z(np.arange(1.0, 10001.0))
+    assert seen == [(1.0, 1001.0, 1001), (5000.0, 10000.0, 5001)]
+    seen.clear()
+    summaries.geweke_z(np.arange(1.0, 41.0))                     # n = 40: 1..ceiling(4.9) = 5 and floor(20.5) = 20..40
+    assert seen == [(1.0, 5.0, 5), (20.0, 40.0, 21)]
+
+
 def test_rhat_from_moments_equals_rhat_from_draws():
     x = np.random.default_rng(1).normal(size=(5, 300, 3)) + np.arange(5)[:, None, None] * 0.1
     np.testing.assert_allclose(summaries.rhat_from_moments(*summaries.chain_moments(x)), summaries.rhat_per_parameter(x))

@@ -177,7 +177,10 @@ def test_run_IFRmodel_age_api_shapes(built_lib, modfit):
     assert list(out.columns[:6]) == ["chain", "rung", "iteration", "stage", "logprior", "loglikelihood"]
     assert list(out.columns[6:]) == spec.names
     assert len(out) == 2 * 2 * 80 and set(out["stage"]) == {"burnin", "sampling"}
-    first = out[(out["chain"] == "chain1") & (out["rung"] == "rung2") & (out["iteration"] == 1)]
+    # "rung1" is the cold chain by default: the label every consumer of the reference reads (R/summarize_plot.R:68,164,276,591,687)
+    rd = fit["mcmcout"]["diagnostics"]["rung_details"]
+    assert list(rd["rung"]) == [1, 2] and list(rd["thermodynamic_power"]) == [1.0, 0.0]
+    first = out[(out["chain"] == "chain1") & (out["rung"] == "rung1") & (out["iteration"] == 1)]
     assert first["loglikelihood"].iloc[0] == pytest.approx(-231967.69462831024, rel=1e-12)   # row 1 = init (stored fit)
     assert set(fit["mcmcout"]["diagnostics"]) >= {"rhat", "rung_details", "mc_accept"}
     assert list(fit["mcmcout"]["parameters"]) == ["data", "df_params", "loglike", "logprior", "burnin", "samples", "rungs", "chains",

@@ -47,6 +47,38 @@ def test_reference_unit_test_vectors(built_lib, simdata_binomial, simdata_logit)
         assert m.loglike_scalar(th[0], param_i=3) == ll[0]   # param_i is ignored, like binomial.cpp:7
 
 
+def test_reference_call_shape_params_param_i_data_misc(built_lib, simdata_binomial, simdata_logit):
+    """The static twins' own 4-argument shape (src/RcppExports.cpp:10-35): a NAMED parameter vector plus the data and misc lists,
+    exactly as tests/testthat/test-check_natcub_cpp.R:90-150 calls COVIDCurve:::natcubspline_loglike_binomial / _logit."""
+    from covidcurve_b200 import _lib
+    for (spec, g), binomial in ((simdata_binomial, True), (simdata_logit, False)):
+        misc = dict(rcensor_day=int(g["rcensor_day"]), days_obsd=int(g["days_obsd"]), n_knots=int(g["n_knots"]), n_sero_obs=2,
+                    sero_survey_start=g["sero_survey_start"], sero_survey_end=g["sero_survey_end"],
+                    max_seroday_obsd=int(g["max_seroday_obsd"]), demog=g["demog"], account_serorev=False)
+        data = dict(obs_deaths=g["obs_deaths"], prop_strata_obs_deaths=g["prop_strata_obs_deaths"])
+        data.update(dict(obs_serologypos=g["obs_serologypos"], obs_serologyn=g["obs_serologyn"]) if binomial else
+                    dict(obs_serologymu=g["obs_serologymu"], obs_serologyse=g["obs_serologyse"]))
+        names = [str(n) for n in g["param_names"]]
+        # the test's vectors carry two NA entries "just to make visible to cpp" and are in another order than df_params
+        order = ["mod", "sod", "ma1", "ma2", "ma3", "x1", "x2", "x3", "x4", "y1", "y2", "y3", "y4", "y5", "ne1", "ne2", "ne3", "sens", "spec",
+                 "sero_con_rate"]
+        mk = lambda v: {**{n: float(v[names.index(n)]) for n in order}, "sero_rev_shape": np.nan, "sero_rev_scale": np.nan}
+        more = _lib.natcubspline_loglike(mk(g["morelikely"]), 1, data, misc, binomial=binomial)["LogLik"]
+        less = _lib.natcubspline_loglike(mk(g["lesslikely"]), 1, data, misc, binomial=binomial)["LogLik"]
+        assert more > less                                                   # the reference test's own assertion (:135, :152)
+        want = _oracle(spec).loglike(np.stack([g["morelikely"], g["lesslikely"]]))
+        assert relerr(np.array([more, less]), want) <= TOL
+        assert _lib.natcubspline_loglike(mk(g["morelikely"]), 7, data, misc, binomial=binomial)["LogLik"] == more   # param_i ignored
+        bad = mk(g["morelikely"])
+        del bad["x3"]
+        with pytest.raises(_lib.CCError, match="no element named 'x3'"):
+            _lib.natcubspline_loglike(bad, 1, data, misc, binomial=binomial)
+        # other data -> another cached model, not a stale answer
+        data2 = dict(data, obs_deaths=np.where(g["obs_deaths"] > 0, g["obs_deaths"] + 1, g["obs_deaths"]))
+        assert _lib.natcubspline_loglike(mk(g["morelikely"]), 1, data2, misc, binomial=binomial)["LogLik"] != more
+        assert _lib.natcubspline_loglike(mk(g["morelikely"]), 1, data, misc, binomial=binomial)["LogLik"] == more
+
+
 @pytest.mark.parametrize("cfg,kw", [
     ("cfg2", {}), ("cfg2", dict(reparam=True)), ("cfg2", dict(binomial=True)),
     ("cfg3", {}), ("cfg3", dict(serorev=True)), ("cfg3", dict(reparam=True)), ("cfg4", {}), ("cfg4", dict(serorev=True, binomial=False)),
