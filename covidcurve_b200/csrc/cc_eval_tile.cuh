@@ -24,10 +24,10 @@ struct RecLayout {
 __host__ __device__ inline RecLayout rec_layout(int K, int A, int S) {
   RecLayout L;
   L.flags = 0;            // 1 = knots ordered
-  L.gam = 1;              // alph, scale, h, lgam_a, lsc, km, nser, QT, fast
-  L.sero = 10;            // rate, g1, g32, fac | rate, shape, lws, badw
-  L.snm = 14;
-  L.ne = 15;              // [A]
+  L.gam = 1;              // alph, scale, h, lgam_a, lsc, km, nser, QT, fast, lgam_a1, logA, exp(-h), k_hi
+  L.sero = 14;            // rate, g1, g32, fac | rate, shape, lws, badw
+  L.snm = 18;
+  L.ne = 19;              // [A]
   L.spl = L.ne + A;       // per interval j < K-1: x_j, y_j, sp1_j, sp2_j, sp3_j
   L.cday = L.spl + 5 * (K - 1);  // cday[1..K-2]
   L.n2 = L.cday + (K - 2);
@@ -257,6 +257,15 @@ __device__ inline void p1_gamma(const KModel& m, const RecLayout& L, Par par, Pu
   }
   put(L.gam + 0, alph); put(L.gam + 1, scale); put(L.gam + 2, h); put(L.gam + 3, lgam_a); put(L.gam + 4, lsc);
   put(L.gam + 5, (double)km); put(L.gam + 6, (double)nser); put(L.gam + 7, QT); put(L.gam + 8, fast ? 1.0 : 0.0);
+  // per-vector scalars of the per-day pass, computed once here instead of by every lane of the warp there
+  double lgam_a1 = 0.0, logA = 0.0, emh = 0.0, k_hi = 0.0;
+  if (fast) {
+    lgam_a1 = lgam_a + log(alph);
+    logA = log(fmax(1.0, fabs(alph - 1.0)));
+    emh = exp(-h);
+    k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;  // masses beyond this day are < 2^-54 of the total: exactly zero
+  }
+  put(L.gam + 9, lgam_a1); put(L.gam + 10, logA); put(L.gam + 11, emh); put(L.gam + 12, k_hi);
 }
 
 // sero constants (binomial.cpp:257-284)
@@ -304,30 +313,57 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
   // number of interval-mass coefficients: the scaled coefficients c'_m = c_m / x_{km+1}^m decay like P(m+1, h)
   const int nct = (h <= 3.6) ? 32 : (h <= 16.0) ? 64 : (h <= 32.0) ? 96 : 128;
   if (fast && km < T) {
-    // c'_m = binom(a-1, m) (km+1)^-m * h e^-h sigma_m,  sigma_m = sum_j h^j / ((m+1)...(m+1+j));  lane holds m = lane + 32 g
-    const double emh = exp(-h), rk1 = tb.rk[km + 1];
-    double carry = 1.0, c0 = 0.0, clast = 0.0;
-    for (int g = 0; g < (nct >> 5); g++) {
-      const int mm = lane + 32 * g;
-      double term = tb.rk[mm + 1], sum = term;
-      int j = 1;
-      while (__any_sync(0xffffffffu, term > 1e-18 * sum) && j < 400) {
-        term *= h * ((mm + 1 + j < tb.nrk) ? tb.rk[mm + 1 + j] : m.rk[mm + 1 + j]);
+    // c'_m = binom(a-1, m) (km+1)^-m * h e^-h sigma_m,  sigma_m = sum_j h^j / ((m+1)...(m+1+j));  lane holds m = lane + 32 g.
+    // sigma obeys sigma_m = (1 + h sigma_{m+1}) / (m+1): ONE short series at m = nct (ratio h / (nct + j) <= 3/8), then the
+    // recurrence downwards as a warp scan over affine maps, 32 values per round (errors shrink going down).  A series per
+    // lane - up to 100 rounds of a dependent multiply-add for every group at large h - was 8 % of the box workload.
+    const double emh = w.rec[L.gam + 11], rk1 = tb.rk[km + 1];
+    const int ng = nct >> 5;
+    double sig_next;
+    {
+      double term = m.rk[nct + 1], sum = term;
+      for (int j = 1; j < 200 && term > 1e-18 * sum; j++) {
+        term *= h * m.rk[nct + 1 + j];
         sum += term;
-        j++;
       }
-      double bn = (mm >= 1) ? (alph - (double)mm) * tb.rk[mm] * rk1 : 1.0;  // inclusive prefix product -> binom(a-1, m) (km+1)^-m
+      sig_next = sum;
+    }
+    double sig[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double t1 = __shfl_up_sync(0xffffffffu, bn, o);
-        if (lane >= o) bn *= t1;
+    for (int g = 3; g >= 0; g--) {
+      if (g < ng) {
+        const int mm = lane + 32 * g;
+        double a = tb.rk[mm + 1], b = h * a;  // sigma_m = a + b sigma_{m+1}
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double a2 = __shfl_down_sync(0xffffffffu, a, o), b2 = __shfl_down_sync(0xffffffffu, b, o);
+          if (lane + o < 32) {
+            a = fma(b, a2, a);
+            b *= b2;
+          }
+        }
+        sig[g] = fma(b, sig_next, a);
+        sig_next = __shfl_sync(0xffffffffu, sig[g], 0);
       }
-      bn *= carry;
-      carry = __shfl_sync(0xffffffffu, bn, 31);
-      const double cm = bn * (h * emh * sum);
-      ctab[mm] = cm;
-      if (g == 0) c0 = __shfl_sync(0xffffffffu, cm, 0);
-      clast = __shfl_sync(0xffffffffu, cm, 31);
+    }
+    double carry = 1.0, c0 = 0.0, clast = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      if (g < ng) {
+        const int mm = lane + 32 * g;
+        double bn = (mm >= 1) ? (alph - (double)mm) * tb.rk[mm] * rk1 : 1.0;  // inclusive prefix product -> binom(a-1, m) (km+1)^-m
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double t1 = __shfl_up_sync(0xffffffffu, bn, o);
+          if (lane >= o) bn *= t1;
+        }
+        bn *= carry;
+        carry = __shfl_sync(0xffffffffu, bn, 31);
+        const double cm = bn * (h * emh * sig[g]);
+        ctab[mm] = cm;
+        if (g == 0) c0 = __shfl_sync(0xffffffffu, cm, 0);
+        clast = __shfl_sync(0xffffffffu, cm, 31);
+      }
     }
     if (!(fabs(clast) <= 1e-18 * c0)) fast = false;  // table not converged at the first upper day
   }
@@ -347,9 +383,9 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
     // upper part: interval masses for k = km+1 .. T-1, written to P[k]; two days per lane and round.
     // I(x_k) = sum_m c'_m v^m with v = (km+1)/k; terms beyond M are below e^-41.5 of the leading one ((A/k)^m decay)
     const double A = fmax(1.0, fabs(alph - 1.0));
-    const double k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;             // masses beyond are < 2^-54 of the total: 0
+    const double k_hi = w.rec[L.gam + 12];                                    // masses beyond are < 2^-54 of the total: 0
     const int kend = (k_hi >= (double)T) ? T : min(T, (int)k_hi + 2);
-    const double kp1 = (double)(km + 1), logA = log(A);
+    const double kp1 = (double)(km + 1), logA = w.rec[L.gam + 10];
     int Mr = nct;  // series length of round `lane` (64 days per round)
     {
       const int k0 = km + 1 + 64 * lane;
@@ -373,13 +409,13 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
         Ib = fma(Ib, vb, cq);
       }
       const double am1 = alph - 1.0;
-      const double fa = exp(am1 * (tb.logk[kac] - lsc) - (double)ka * h - lgam_a);
-      const double fb = exp(am1 * (tb.logk[kbc] - lsc) - (double)kb * h - lgam_a);
+      double fa, fb;
+      cc_exp2(am1 * (tb.logk[kac] - lsc) - (double)ka * h - lgam_a, am1 * (tb.logk[kbc] - lsc) - (double)kb * h - lgam_a, fa, fb);
       if (ka < T) P[ka] = fa * Ia;
       if (kb < T) P[kb] = fb * Ib;
     }
     // lower part: series, days 1..km
-    const double lgam_a1 = lgam_a + log(alph);
+    const double lgam_a1 = w.rec[L.gam + 9];
     for (int k0 = 1; k0 <= km; k0 += 32) {
       const int k = k0 + lane;
       const double x = (double)k * h;
@@ -389,7 +425,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
       const double E = alph * lx - x - lgam_a1;
       double pv;
       if (E > -690.0 || !(alph > 1.0)) {
-        pv = exp(E) * ssum;
+        pv = cc_exp(E) * ssum;
       } else {
         // Below DBL_MIN / DBL_EPSILON R's pgamma_raw recomputes the value in log space and applies ONE exp, so a subnormal
         // result is rounded once, from the exact value: do the same (log P = E + log(series))
@@ -466,8 +502,8 @@ __device__ inline void tile_sero_prefix(const KModel& m, const RecLayout& L, con
   for (int k = lane; k < 64 * NT; k += 32) {
     double c = 0.0, sv = 0.0;
     if (k < M) {
-      c = rr * exp(-(double)(k + 1) / rate);
-      sv = badw ? d_nan() : ((k == 0) ? 1.0 : exp(-exp(shape * (tb.logk[k] - lws))));
+      c = rr * cc_exp(-(double)(k + 1) / rate);
+      sv = badw ? d_nan() : ((k == 0) ? 1.0 : cc_exp(-cc_exp(shape * (tb.logk[k] - lws))));
     }
     w.xs[xs_index(k)] = c;
     w.gs[7 + k] = sv;
@@ -520,6 +556,13 @@ __device__ __forceinline__ void warp_sum4(double& a, double& b, double& c, doubl
   }
 }
 
+// knot vectors longer than K = 5: interval thresholds beyond the three kept in registers (out of line: never runs at K = 5)
+__device__ __noinline__ int spline_interval_beyond3(const double* cday, int K, double di) {
+  int j = 0;
+  for (int mI = 3; mI < K - 2; mI++) j += (cday[mI] < di) ? 1 : 0;
+  return j;
+}
+
 // ---- S5 infection curve: w.xs <- exp(spline) (zero beyond T); returns the warp-reduced total
 template <int NT>
 __device__ inline double stage_spline(const KModel& m, const RecLayout& L, const double* __restrict__ rec, double* __restrict__ xs) {
@@ -527,24 +570,26 @@ __device__ inline double stage_spline(const KModel& m, const RecLayout& L, const
   double tot = 0.0;
   // interval thresholds in registers (the common K = 5 has three); longer knot vectors fall back to shared memory
   const double cd0 = (K > 2) ? rec[L.cday] : 1e300, cd1 = (K > 3) ? rec[L.cday + 1] : 1e300, cd2 = (K > 4) ? rec[L.cday + 2] : 1e300;
-  const double y0 = rec[L.spl + 1];
   // two days per lane and round, branch-free (days beyond T are evaluated at T - 1 and zeroed): the two exp() chains are
   // adjacent in the instruction stream and the compiler interleaves them
 #pragma unroll 1
   for (int i0 = lane; i0 < 64 * NT; i0 += 64) {
-    double v[2];
+    double v[2], y[2];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int i = i0 + 32 * u, ic = min(i, T - 1);
       const double di = (double)ic;
       int j = ((cd0 < di) ? 1 : 0) + ((cd1 < di) ? 1 : 0) + ((cd2 < di) ? 1 : 0);
-      for (int mI = 3; mI < K - 2; mI++) j += (rec[L.cday + mI] < di) ? 1 : 0;
+      if (K > 5) j += spline_interval_beyond3(rec + L.cday, K, di);
       const double* c = rec + L.spl + 5 * j;
       const double dx = (double)(ic + 1) - c[0];
-      const double y = (ic == 0) ? y0 : fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
-      const double ev = exp(y);
-      v[u] = (i < T) ? ev : 0.0;
+      // day 1 (ic == 0) lies in interval 0 whose left knot is exactly 1, so dx = 0 and the cubic returns its constant term
+      // node_y[0] - binomial.cpp:144 - without a special case (with non-finite coefficients the evaluation fails either way)
+      y[u] = fma(fma(fma(c[4], dx, c[3]), dx, c[2]), dx, c[1]);
     }
+    cc_exp2(y[0], y[1], v[0], v[1]);
+    v[0] = (i0 < T) ? v[0] : 0.0;
+    v[1] = (i0 + 32 < T) ? v[1] : 0.0;
     tot += v[0];
     tot += v[1];
     xs[xs_index(i0)] = v[0];
@@ -585,9 +630,8 @@ __device__ __noinline__ void conv_fixup_tiny(int T, const double* __restrict__ x
 // out there are skipped without changing a bit (short delays: most of the triangle for sod < 0.5).
 __device__ inline int conv_lag_blocks(const KModel& m, const RecLayout& L, const double* rec) {
   const int nb = (m.T + 7) >> 3;
-  const double alph = rec[L.gam + 0], scale = rec[L.gam + 1];
-  if (rec[L.gam + 8] == 0.0 || !(alph > 0.0) || !(scale > 0.0)) return nb;  // general algorithm: keep everything
-  const double k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;
+  if (rec[L.gam + 8] == 0.0) return nb;  // general algorithm: keep everything
+  const double k_hi = rec[L.gam + 12];
   if (!(k_hi < (double)m.T)) return nb;
   const int kend = (int)k_hi + 2;                     // first day whose mass is exactly zero (tile_gamma)
   return min(nb, ((kend + 14) >> 3) + 1);            // block dl holds lags 8 dl - 7 .. 8 dl + 7
@@ -696,18 +740,33 @@ __device__ inline L1Sums stage_l1_sums(const KModel& m, const TileTables& tb, co
 // ---- S11/S12 survey-window means of infxn (*) H through the prefix-summed hazard (binomial.cpp:288-311); put(s, mean)
 template <typename PutBase>
 __device__ inline void stage_surveys(const KModel& m, const double* __restrict__ xs, const double* __restrict__ sk, PutBase put) {
-  const int lane = threadIdx.x & 31;
-  for (int s = 0; s < m.S; s++) {
-    const int st = m.sero_start[s], en = m.sero_end[s];
-    double b = 0.0;
+  const int lane = threadIdx.x & 31, S = m.S;
+  // surveys three at a time in ONE pass over the series: each incidence value is loaded once and feeds three independent
+  // accumulators (the order of additions within a survey is unchanged: lane-strided partial sums, then the butterfly)
+  for (int s0 = 0; s0 < S; s0 += 3) {
+    const int n = min(3, S - s0);
+    const int st0 = m.sero_start[s0], en0 = m.sero_end[s0];
+    const int st1 = (n > 1) ? m.sero_start[s0 + 1] : 1, en1 = (n > 1) ? m.sero_end[s0 + 1] : 0;
+    const int st2 = (n > 2) ? m.sero_start[s0 + 2] : 1, en2 = (n > 2) ? m.sero_end[s0 + 2] : 0;
+    const int emax = max(en0, max(en1, en2));
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, dummy = 0.0;
 #pragma unroll 2
-    for (int t = lane; t < en; t += 32) {
-      int lo = st - 1 - t;
-      lo = lo < 0 ? 0 : lo;
-      b = fma(xs[xs_index(t)], sk[en - t] - sk[lo], b);
+    for (int t = lane; t < emax; t += 32) {
+      const double x = xs[xs_index(t)];
+      // past a survey's last day the weight is CH[0] - CH[0] = 0 (indices clamped to 0): the term adds nothing
+      const int h0 = max(en0 - t, 0), l0 = max(st0 - 1 - t, 0);
+      const int h1 = max(en1 - t, 0), l1 = max(st1 - 1 - t, 0);
+      const int h2 = max(en2 - t, 0), l2 = max(st2 - 1 - t, 0);
+      if (t < en0) b0 = fma(x, sk[h0] - sk[l0], b0);
+      if (t < en1) b1 = fma(x, sk[h1] - sk[l1], b1);
+      if (t < en2) b2 = fma(x, sk[h2] - sk[l2], b2);
     }
-    b = warp_sum(b);
-    if (lane == 0) put(s, b / (double)(en - st + 1));
+    warp_sum4(b0, b1, b2, dummy);
+    if (lane == 0) {
+      put(s0, b0 / (double)(en0 - st0 + 1));
+      if (n > 1) put(s0 + 1, b1 / (double)(en1 - st1 + 1));
+      if (n > 2) put(s0 + 2, b2 / (double)(en2 - st2 + 1));
+    }
   }
 }
 
