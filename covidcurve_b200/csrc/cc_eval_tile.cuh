@@ -308,7 +308,7 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
   double* P = w.gs + 7;
   double* tab = w.xs + kXsLead;
   double* ctab = w.ctab;
-  const double kLogTol = 41.5;
+  const double kLogTol = 36.5;  // interval-mass series truncated below e^-36.5 = 1.4e-16 of the leading term
 
   // number of interval-mass coefficients: the scaled coefficients c'_m = c_m / x_{km+1}^m decay like P(m+1, h)
   const int nct = (h <= 3.6) ? 32 : (h <= 16.0) ? 64 : (h <= 32.0) ? 96 : 128;
@@ -569,7 +569,10 @@ __device__ inline double stage_spline(const KModel& m, const RecLayout& L, const
   const int lane = threadIdx.x & 31, T = m.T, K = m.K;
   double tot = 0.0;
   // interval thresholds in registers (the common K = 5 has three); longer knot vectors fall back to shared memory
-  const double cd0 = (K > 2) ? rec[L.cday] : 1e300, cd1 = (K > 3) ? rec[L.cday + 1] : 1e300, cd2 = (K > 4) ? rec[L.cday + 2] : 1e300;
+  // (integer-valued by construction, p1_spline; compared as integers: a double compare costs a slot of the FP64 pipe)
+  auto as_day = [](double c) { return (c < 2.0e9) ? (int)c : 0x7fffffff; };
+  const int cd0 = (K > 2) ? as_day(rec[L.cday]) : 0x7fffffff, cd1 = (K > 3) ? as_day(rec[L.cday + 1]) : 0x7fffffff,
+            cd2 = (K > 4) ? as_day(rec[L.cday + 2]) : 0x7fffffff;
   // two days per lane and round, branch-free (days beyond T are evaluated at T - 1 and zeroed): the two exp() chains are
   // adjacent in the instruction stream and the compiler interleaves them
 #pragma unroll 1
@@ -579,7 +582,7 @@ __device__ inline double stage_spline(const KModel& m, const RecLayout& L, const
     for (int u = 0; u < 2; u++) {
       const int i = i0 + 32 * u, ic = min(i, T - 1);
       const double di = (double)ic;
-      int j = ((cd0 < di) ? 1 : 0) + ((cd1 < di) ? 1 : 0) + ((cd2 < di) ? 1 : 0);
+      int j = ((cd0 < ic) ? 1 : 0) + ((cd1 < ic) ? 1 : 0) + ((cd2 < ic) ? 1 : 0);
       if (K > 5) j += spline_interval_beyond3(rec + L.cday, K, di);
       const double* c = rec + L.spl + 5 * j;
       const double dx = (double)(ic + 1) - c[0];
@@ -677,7 +680,8 @@ __device__ inline void stage_l1_direct(const KModel& m, const TileTables& tb, do
     const bool unc = (j + 1) < m.rcensor_day, use = unc && (x != -1);
     const double lg = fast_log_normal(expd, m.logtab);
     const double lp = (x > 0) ? fma((double)x, lg, -expd) : -expd;  // - lgamma(x+1) is data only: m.l1_const
-    odd |= (use && (!fast_log_ok(expd) || x < 0)) ? 1 : 0;
+    // not a positive normal mean (one unsigned compare on the high word), or a negative count
+    odd |= (use && (((unsigned)(__double2hiint(expd) - 0x00100000) >= 0x7fe00000u) || x < 0)) ? 1 : 0;
     s_all += expd;
     s_unc += unc ? a : 0.0;
     l1 += use ? lp : 0.0;
