@@ -85,6 +85,7 @@ struct McmcState {
   double* rec_lp;
   // cached evaluation state of every particle's current parameter vector (layout: sweep_cache_layout), zero = not built yet
   double* cache;
+  int* ticket;        // particle queue of the sweep kernel (reset before every launch)
 };
 
 }  // namespace ccdev

@@ -380,7 +380,6 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
   for (int i = lane; i < kXsLead; i += 32) w.xs[i] = 0.0;  // the zeros in front of the series and of the delay kernel are
   if (lane < 7) w.gs[lane] = 0.0;                          // never overwritten (full-array copies carry them along)
   __syncwarp();
-  const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
   const int P = s.n_chains * s.rungs;
   const bool adapt = s.adapt_in_sampling || iteration <= s.burnin;
   // tile_gamma keeps its coefficient table in the (not yet written) convolution output buffer and its reciprocal table
@@ -420,13 +419,24 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
     asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");
 #endif
   };
-  for (int b0 = 0; b0 < P; b0 += nwarps) {
-    const int b = b0 + gwarp;
-    if (b >= P) {  // no particle left for this warp in the last round: keep the CTA's barrier count
+  // Particles are handed out dynamically, one per warp of the CTA and ticket, in rung-major order starting with the hottest
+  // rung: the warps of a CTA then hold neighbouring chains at the SAME temperature (similar acceptance rates and validity,
+  // hence similar work between the per-update barriers), the expensive particles go first and CTAs that drew cheap ones
+  // come back for more - the sweep ends within one particle of the ideal instead of one static round.
+  __shared__ int s_q0;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_q0 = atomicAdd(s.ticket, wpc);
+    __syncthreads();
+    const int q = s_q0 + warp;
+    if (s_q0 >= P) break;
+    if (q >= P) {  // no particle left for this warp in the last chunk: keep the CTA's barrier count
       for (int i = 0; i < d; i++) cta_bar();
       continue;
     }
-    const int c = b / s.rungs, r = b - c * s.rungs;
+    const int ro = q / s.n_chains, c = q - ro * s.n_chains;
+    const int r = (s.cold_pos == 0) ? (s.rungs - 1 - ro) : ro;  // hot end of the ladder first
+    const int b = c * s.rungs + r;
     const int pid = s.at_rung[b];  // particle (within chain) sitting at rung position r
     const int p = c * s.rungs + pid;
     const int slot = s.bw_per_particle ? p : b;
@@ -500,11 +510,18 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
       }
       __syncwarp();
       const bool valid = w.recB[L.flags] != 0.0;
-      const bool from_invalid = (w.recA[L.flags] == 0.0) || (w.recA[L.o_status] != 0.0);  // no usable caches: redo everything
-      const bool do_sero = valid && ((dep & kDepSero) || from_invalid);
-      const bool do_gamma = valid && ((dep & kDepGamma) || from_invalid);
-      const bool do_spline = valid && ((dep & kDepSpline) || from_invalid);
-      const bool need_conv = do_spline || do_gamma, need_surv = do_spline || do_sero;
+      // What the cache holds for the current state.  Knots out of order (or nothing built yet): no per-day array at all.
+      // Population check failed (binomial.cpp:170-184): the hazard prefix sums, the delay kernel and the series WERE built
+      // and committed - they precede the check - only what follows it (convolution, Poisson sums, survey sums, age split,
+      // serology term) is missing.  The hot rung (beta = 0) accepts such states all the time; redoing every stage from them
+      // made its particles five times as expensive as the others and, with one warp per particle, the critical path of
+      // the whole sweep.
+      const bool cur_noarrays = (w.recA[L.flags] == 0.0);
+      const bool from_invalid = cur_noarrays || (w.recA[L.o_status] != 0.0);  // nothing downstream of the check is cached
+      const bool do_sero = valid && ((dep & kDepSero) || cur_noarrays);
+      const bool do_gamma = valid && ((dep & kDepGamma) || cur_noarrays);
+      const bool do_spline = valid && ((dep & kDepSpline) || cur_noarrays);
+      const bool need_conv = do_spline || do_gamma || from_invalid, need_surv = do_spline || do_sero || from_invalid;
       bool new_auc = false;
       double tot_p = tot_cur;
       L1Sums sums_p = sums_cur;
@@ -769,7 +786,13 @@ static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
   if (nt == NT_) {                                                                                                    \
     e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes / kWarpsPerCta * p2_warps(NT_)); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_sweep_cached_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    if (e == cudaSuccess) {                                                                                           \
+      cudaFuncAttributes fa;                                                                                          \
+      e = cudaFuncGetAttributes(&fa, mcmc_sweep_cached_kernel<NT_>);                                                  \
+      if (e == cudaSuccess)                                                                                           \
+        e = cudaFuncSetAttribute(mcmc_sweep_cached_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                 227 * 1024 - (int)fa.sharedSizeBytes);                                               \
+    }                                                                                                                 \
   }
   CC_FOR_EACH_NT(CC_OPT)
 #undef CC_OPT
@@ -1558,7 +1581,7 @@ extern "C" int cc_mcmc_create(cc_model* m, const cc_mcmc_opts* o, cc_mcmc** out)
       (rc = dalloc(r, &s.swap_acc, (size_t)C * std::max(R - 1, 1))) || (rc = dalloc(r, &s.swap_try, (size_t)C * std::max(R - 1, 1))) ||
       (rc = dalloc(r, &s.rec_theta, rec * d, false)) || (rc = dalloc(r, &s.rec_ll, rec, false)) ||
       (rc = dalloc(r, &s.rec_lp, rec, false)) ||
-      (rc = dalloc(r, &s.cache, P * (size_t)sweep_cache_layout(m->k.K, m->k.A, m->k.S, m->nt).size))) {
+      (rc = dalloc(r, &s.cache, P * (size_t)sweep_cache_layout(m->k.K, m->k.A, m->k.S, m->nt).size)) || (rc = dalloc(r, &s.ticket, 1))) {
     cc_mcmc_destroy(r);
     return rc;
   }
@@ -1670,6 +1693,7 @@ extern "C" int cc_mcmc_advance(cc_mcmc* r, int32_t n_iter) {
   for (int k = 0; k < n_iter; k++) {
     if (r->iteration >= total) return fail(CC_E_STATE, "cc_mcmc_advance: burnin + samples iterations already done");
     const int it = (int)(r->iteration + 1);
+    CC_CUDA(cudaMemsetAsync(s.ticket, 0, sizeof(int), m->stream));
     switch (m->nt) {
 #define CC_LAUNCH(NT_) case NT_: mcmc_sweep_cached_kernel<NT_><<<r->sweep_grid, 32 * r->sweep_wpc, r->sweep_smem, m->stream>>>(m->k, s, it); break;
       CC_FOR_EACH_NT(CC_LAUNCH)
