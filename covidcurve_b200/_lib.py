@@ -79,6 +79,12 @@ SYMBOLS = {
     "cc_logprior": (C.c_int, [_vp, c_dp, C.c_int, c_dp]),
     "cc_loglike_call": (C.c_int, [C.POINTER(CallArgs), c_dp, C.c_int, C.c_int, c_dp]),
     "cc_curves_batch": (C.c_int, [_vp, c_dp, C.c_int64, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
+    "cc_post_deaths_batch": (C.c_int, [_vp, c_dp, C.c_int64, C.c_int64, c_dp]),
+    "cc_summarize_draws": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int, _vp, c_dp]),
+    "cc_chain_moments": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp, _vp, _vp]),
+    "cc_gelman_from_moments": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int, _vp, c_dp]),
+    "cc_overall_ifr_draws": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, c_ip, c_ip, c_dp, C.c_int32,
+                                       C.c_int, _vp, _vp]),
     "cc_mcmc_create": (C.c_int, [_vp, C.POINTER(McmcOpts), C.POINTER(_vp)]),
     "cc_mcmc_advance": (C.c_int, [_vp, C.c_int32]),
     "cc_mcmc_last_advance_ms": (C.c_int, [_vp, c_dp]),
@@ -231,6 +237,98 @@ class Model:
         ptr = lambda a: _dp(a) if a is not None else None
         check(self.L.cc_curves_batch(self.h, _dp(soa), n, n, ptr(o["infxn"]), ptr(o["ne"]), ptr(o["auc"]), ptr(o["sero_full"])))
         return {k: v for k, v in o.items() if v is not None}
+
+
+    def post_deaths(self, theta):
+        """cc_post_deaths_batch: expected deaths [n][T][A] per draw with the gamma density kernel (R/summarize_plot.R:605-641)."""
+        soa = self._soa(theta)
+        n = soa.shape[1]
+        out = np.empty((n, self.spec.T, self.spec.A))
+        check(self.L.cc_post_deaths_batch(self.h, _dp(soa), n, n, _dp(out)))
+        return out
+
+
+# ---- posterior summaries on the device (cc_summ.cu).  `draws` is either a numpy array [chains, iterations, params] (uploaded)
+# or a CUDA torch tensor of that shape (any chain / iteration stride, unit parameter stride; used in place)
+SUMM_FIELDS = ("min", "LCI", "median", "mean", "UCI", "max", "ESS", "GewekeZ", "GewekeP", "var", "spec0", "n")
+GELMAN_FIELDS = ("rhat", "psrf", "W", "B", "W_df", "df_adj", "R2_fixed", "R2_random")
+
+
+def _draws_arg(draws):
+    """(pointer, C, n, P, stride_chain, stride_iter, mem, device or None, stream, keepalive)"""
+    if isinstance(draws, np.ndarray) or not hasattr(draws, "data_ptr"):
+        a = np.ascontiguousarray(draws, dtype=np.float64)
+        if a.ndim != 3:
+            raise ValueError("draws must be [chains, iterations, params]")
+        Cn, n, P = a.shape
+        return a.ctypes.data, Cn, n, P, n * P, P, CC_MEM_HOST, None, None, a
+    import torch
+    t = draws
+    if t.ndim != 3 or t.dtype != torch.float64 or not t.is_cuda:
+        raise ValueError("device draws must be a CUDA float64 tensor [chains, iterations, params]")
+    if t.stride(2) != 1:
+        t = t.contiguous()
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    return t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.stride(0), t.stride(1), CC_MEM_DEVICE, t.device.index, stream or None, t
+
+
+def summarize_draws(draws, by_chain=True, device=0):
+    """cc_summarize_draws -> array [groups, params, len(SUMM_FIELDS)] (groups = chains, or 1 when not by_chain)."""
+    ptr, Cn, n, P, sc, si, mem, dev, stream, _keep = _draws_arg(draws)
+    out = np.empty((Cn if by_chain else 1, P, len(SUMM_FIELDS)))
+    check(load().cc_summarize_draws(device if dev is None else dev, ptr, Cn, n, P, sc, si, int(bool(by_chain)), mem, stream, _dp(out)))
+    return out
+
+
+def chain_moments(draws, first_iter=0, device=0):
+    """cc_chain_moments -> (mean, var) [chains, params]; numpy arrays for numpy draws, CUDA tensors for CUDA draws."""
+    ptr, Cn, n, P, sc, si, mem, dev, stream, _keep = _draws_arg(draws)
+    if mem == CC_MEM_HOST:
+        mean, var = np.empty((Cn, P)), np.empty((Cn, P))
+        check(load().cc_chain_moments(device, ptr, Cn, n, P, sc, si, int(first_iter), mem, None, mean.ctypes.data, var.ctypes.data))
+        return mean, var
+    import torch
+    mean = torch.empty((Cn, P), dtype=torch.float64, device=draws.device)
+    var = torch.empty_like(mean)
+    check(load().cc_chain_moments(dev, ptr, Cn, n, P, sc, si, int(first_iter), mem, stream, mean.data_ptr(), var.data_ptr()))
+    return mean, var
+
+
+def gelman_from_moments(mean, var, n_iter_used, device=0):
+    """cc_gelman_from_moments -> array [params, len(GELMAN_FIELDS)] from per-chain moments (numpy or CUDA tensors [chains, params])."""
+    if isinstance(mean, np.ndarray):
+        m, v = np.ascontiguousarray(mean, dtype=np.float64), np.ascontiguousarray(var, dtype=np.float64)
+        Cn, P = m.shape
+        out = np.empty((P, len(GELMAN_FIELDS)))
+        check(load().cc_gelman_from_moments(device, m.ctypes.data, v.ctypes.data, Cn, int(n_iter_used), P, CC_MEM_HOST, None, _dp(out)))
+        return out
+    import torch
+    m, v = mean.contiguous(), var.contiguous()
+    Cn, P = m.shape
+    out = np.empty((P, len(GELMAN_FIELDS)))
+    stream = torch.cuda.current_stream(m.device).cuda_stream
+    check(load().cc_gelman_from_moments(m.device.index, m.data_ptr(), v.data_ptr(), Cn, int(n_iter_used), P, CC_MEM_DEVICE, stream or None, _dp(out)))
+    return out
+
+
+def overall_ifr_draws(draws, idx_ifr, popN, idx_noise=None, device=0):
+    """cc_overall_ifr_draws -> est [chains, iterations] (numpy for numpy draws, a CUDA tensor for CUDA draws)."""
+    ptr, Cn, n, P, sc, si, mem, dev, stream, _keep = _draws_arg(draws)
+    ii = np.ascontiguousarray(idx_ifr, dtype=np.int32)
+    nn = None if idx_noise is None else np.ascontiguousarray(idx_noise, dtype=np.int32)
+    pop = np.ascontiguousarray(popN, dtype=np.float64)
+    if pop.size != ii.size or (nn is not None and nn.size != ii.size):
+        raise ValueError("idx_ifr, idx_noise and popN must have one entry per stratum")
+    if mem == CC_MEM_HOST:
+        est = np.empty((Cn, n))
+        check(load().cc_overall_ifr_draws(device, ptr, Cn, n, P, sc, si, _ip(ii), None if nn is None else _ip(nn), _dp(pop), ii.size, mem, None,
+                                          est.ctypes.data))
+        return est
+    import torch
+    est = torch.empty((Cn, n), dtype=torch.float64, device=draws.device)
+    check(load().cc_overall_ifr_draws(dev, ptr, Cn, n, P, sc, si, _ip(ii), None if nn is None else _ip(nn), _dp(pop), ii.size, mem, stream,
+                                      est.data_ptr()))
+    return est
 
 
 class Mcmc:

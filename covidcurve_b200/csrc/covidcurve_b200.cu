@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/covidcurve_b200.h"
+#include "cc_internal.h"
 #include "cc_eval.cuh"
 #include "cc_eval_warp.cuh"
 #include "cc_eval_tile.cuh"
@@ -39,6 +40,8 @@ static int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess)                                                                                 \
       return fail(CC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
   } while (0)
+
+int cc_set_error(int code, const std::string& msg) { return fail(code, msg); }
 
 extern "C" const char* cc_last_error(void) { return g_err.c_str(); }
 extern "C" int cc_abi_version(void) { return CC_ABI_VERSION; }
@@ -647,7 +650,7 @@ __global__ void logprior_batch_kernel(const KModel m, const double* __restrict__
 __global__ void __launch_bounds__(kEvalThreads) curves_kernel(const KModel m, const double* __restrict__ theta, long long n,
                                                               long long ld, double* __restrict__ o_infxn,
                                                               double* __restrict__ o_ne, double* __restrict__ o_auc,
-                                                              double* __restrict__ o_sero) {
+                                                              double* __restrict__ o_sero, double* __restrict__ o_deaths) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // curves need the hazard over all T days (summarize_plot.R:733-771), so carve with M = T
   KModel mc = m;
@@ -678,6 +681,23 @@ __global__ void __launch_bounds__(kEvalThreads) curves_kernel(const KModel m, co
         __syncthreads();
       }
       for (int i = threadIdx.x; i < T; i += blockDim.x) o_sero[v * T + i] = have ? sm.tmp1[i] : d_nan();
+    }
+    if (o_deaths) {
+      // posterior_check_infxns_to_death (R/summarize_plot.R:605-641): gamma DENSITY lookup, then per (day, stratum) the sum over
+      // infection days in the reference's order, every product rounded like its `a * b * c` (no contraction)
+      __syncthreads();
+      const double sod = sm.p[m.idx_sod], mod = sm.p[m.idx_mod];
+      const double shape = 1 / (sod * sod), scale = mod * (sod * sod);
+      for (int k = threadIdx.x; k <= T; k += blockDim.x) sm.pg[k] = dgamma_density((double)k, shape, scale);
+      __syncthreads();
+      auto par = [&](int r) { return sm.p[r]; };
+      for (int o = threadIdx.x; o < T * A; o += blockDim.x) {
+        const int j = o / A, a = o - j * A;
+        const double nea = sm.sc->ne[a], ifr = ifr_of(m, par, a);
+        double acc = 0.0;
+        for (int i = 0; i <= j; i++) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(__dmul_rn(nea, sm.infxn[i]), ifr), sm.pg[j - i]));
+        o_deaths[(v * T + j) * A + a] = have ? acc : d_nan();
+      }
     }
   }
 }
@@ -1456,7 +1476,7 @@ extern "C" int cc_curves_batch(cc_model* m, const double* theta, int64_t n, int6
                           cudaMemcpyHostToDevice, m->stream);
   if (e == cudaSuccess) {
     const size_t smem = eval_smem_bytes(d, T, T);
-    curves_kernel<<<(unsigned)std::min<long long>(n, 65535LL * 16), kEvalThreads, smem, m->stream>>>(k, dth, n, n, di, dn, da, ds);
+    curves_kernel<<<(unsigned)std::min<long long>(n, 65535LL * 16), kEvalThreads, smem, m->stream>>>(k, dth, n, n, di, dn, da, ds, nullptr);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess && infxn) e = cudaMemcpyAsync(infxn, di, (size_t)n * T * sizeof(double), cudaMemcpyDeviceToHost, m->stream);
@@ -1466,6 +1486,35 @@ extern "C" int cc_curves_batch(cc_model* m, const double* theta, int64_t n, int6
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
   cleanup();
   if (e != cudaSuccess) return fail(CC_E_CUDA, std::string("cc_curves_batch: ") + cudaGetErrorString(e));
+  return CC_OK;
+}
+
+extern "C" int cc_post_deaths_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* deaths) {
+  if (!m || !theta || !deaths) return fail(CC_E_INVALID, "cc_post_deaths_batch: null argument");
+  if (n < 0 || ld < n) return fail(CC_E_INVALID, "cc_post_deaths_batch: need 0 <= n <= ld");
+  if (n == 0) return CC_OK;
+  CC_CUDA(cudaSetDevice(m->device));
+  const KModel& k = m->k;
+  const int d = k.d, T = k.T, A = k.A;
+  double *dth = nullptr, *dd = nullptr;
+  const size_t nout = (size_t)n * T * A * sizeof(double);
+  cudaError_t e = cudaMalloc((void**)&dth, (size_t)d * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dd, nout);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(dth, (size_t)n * sizeof(double), theta, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), (size_t)d,
+                          cudaMemcpyHostToDevice, m->stream);
+  if (e == cudaSuccess) {
+    const size_t smem = eval_smem_bytes(d, T, T);
+    curves_kernel<<<(unsigned)std::min<long long>(n, 65535LL * 16), kEvalThreads, smem, m->stream>>>(k, dth, n, n, nullptr, nullptr, nullptr,
+                                                                                                   nullptr, dd);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(deaths, dd, nout, cudaMemcpyDeviceToHost, m->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  else cudaStreamSynchronize(m->stream);
+  cudaFree(dth);
+  cudaFree(dd);
+  if (e != cudaSuccess) return fail(CC_E_CUDA, std::string("cc_post_deaths_batch: ") + cudaGetErrorString(e));
   return CC_OK;
 }
 

@@ -94,6 +94,22 @@ __device__ __forceinline__ double dpois_raw(double x, double lambda) {
   return exp(-stirlerr(x) - bd0(x, lambda)) * rsqrt(CC_2PI * x);
 }
 
+// R::dgamma(x, shape, scale, log = FALSE) (nmath/dgamma.c): the density kernel of posterior_check_infxns_to_death,
+// R/summarize_plot.R:609
+__device__ __forceinline__ double dgamma_density(double x, double shape, double scale) {
+  if (isnan(x) || isnan(shape) || isnan(scale)) return x + shape + scale;
+  if (shape < 0 || scale <= 0) return d_nan();
+  if (x < 0) return 0.0;
+  if (shape == 0) return (x == 0) ? d_inf() : 0.0;
+  if (x == 0) {
+    if (shape < 1) return d_inf();
+    if (shape > 1) return 0.0;
+    return 1 / scale;
+  }
+  if (shape < 1) return dpois_raw(shape, x / scale) * shape / x;
+  return dpois_raw(shape - 1, x / scale) / scale;
+}
+
 // R::dpois(x, lambda, log = TRUE) for integer-valued x (obs deaths are ints in the reference, binomial.cpp:204)
 __device__ __forceinline__ double dpois_log_int(double x, double lambda) {
   if (isnan(lambda)) return lambda;

@@ -88,6 +88,37 @@ def rhat_torch(draws):
     return torch.sqrt(V / W)
 
 
+def gelman_allgather(local, chains: int, confidence: float = 0.95, autoburnin: bool = True, group=None):
+    """coda::gelman.diag and drjacoby's rhat over ALL ranks' chains without moving a draw: each rank reduces its CUDA tensor
+    draws[chain_local, iteration, param] to per-chain means and variances with the library's kernel (cc_chain_moments), the
+    ranks all-gather those 2 x chains x params numbers (NCCL), and every rank finishes with cc_gelman_from_moments.
+    Returns (point estimate, upper limit, drjacoby rhat) - the same values as summaries.device_gelman_diag on gathered draws."""
+    import torch
+    from . import _lib
+    from .summaries import gelman_from_chain_moments
+    n = local.shape[1]
+    first = n // 2 if autoburnin else 0
+    mean, var = _lib.chain_moments(local, first_iter=first)
+    both = torch.stack([mean, var], dim=1)                     # [chain_local, 2, param]
+    allm = allgather_draws(both, chains, group=group)
+    return gelman_from_chain_moments(allm[:, 0, :].contiguous(), allm[:, 1, :].contiguous(), n - first, confidence)
+
+
+def cred_intervals_allgather(local, chains: int, names, chain_offset: int = 0, group=None):
+    """get_cred_intervals(by_chain = TRUE) for all chains of a sharded run: every rank summarises its own chains on its GPU
+    (cc_summarize_draws) and only the 9-number rows travel (all-gather of [chain_local, param, field])."""
+    import pandas as pd
+    import torch
+    from . import _lib
+    tab = torch.from_numpy(_lib.summarize_draws(local, by_chain=True)).to(local.device)
+    allt = allgather_draws(tab, chains, group=group).cpu().numpy()
+    G, P = allt.shape[:2]
+    cols = {"chain": np.repeat(np.arange(1, G + 1), P), "param": np.tile(np.asarray(list(names), dtype=object), G)}
+    for f, c in enumerate(_lib.SUMM_FIELDS[:9]):
+        cols[c] = allt[:, :, f].reshape(-1)
+    return pd.DataFrame(cols)
+
+
 def draws_tensor(mcmc, device):
     """Zero-copy torch view of the recorded draws of a covidcurve_b200._lib.Mcmc run that still lives on `device`:
     theta [chains_local, recorded rungs, rows_cap, d] (only the first `mcmc.rows` rows are valid)."""

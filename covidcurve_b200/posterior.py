@@ -7,7 +7,7 @@ by one (`Rcpp::cppFunction` + `purrr::map`); here the same intermediates come ou
 
   draw_posterior_infxn_cubic_splines   :276-585   ne[a] * infxn[t] per draw (per stratum, or summed)
   draw_posterior_sero_curves           :687-884   seroconverted numbers, crude and test-adjusted prevalence over ALL days
-  posterior_check_infxns_to_death      :591-680   expected deaths per stratum with the gamma DENSITY kernel
+  posterior_check_infxns_to_death      :591-680   expected deaths per stratum with the gamma DENSITY kernel (cc_post_deaths_batch)
 """
 from __future__ import annotations
 
@@ -106,23 +106,25 @@ def draw_posterior_sero_curves(IFRmodel_inf, whichrung=None, dwnsmpl=100, by_cha
 
 def posterior_check_infxns_to_death(IFRmodel_inf, whichrung=None, dwnsmpl=100, by_chain=False, seed=1, device=0):
     """R/summarize_plot.R:591: expected deaths per stratum and day for each down-sampled draw,
-    deaths[j][a] = sum_{i <= j} infxns[i][a] * ifr[a] * dgamma(j - i; 1/sod^2, mod sod^2)  (the DENSITY, :605-641).
-    Runs on the host: it is executed once per down-sampled draw, not per proposal."""
-    from scipy import stats
-    cd = draw_posterior_infxn_cubic_splines(IFRmodel_inf, whichrung, dwnsmpl, by_chain, True, seed, device)["curvedata"]
-    m = IFRmodel_inf["inputs"]["IFRmodel"]
-    T = int(cd["time"].max())
-    frames = []
-    keys = ["chain", "sim"] if by_chain else ["sim"]
-    for key, g in cd.groupby(keys, sort=False):
-        g = g.sort_values("time")
-        mod, sod = float(g[m.modparam].iloc[0]), float(g[m.sodparam].iloc[0])
-        kern = stats.gamma.pdf(np.arange(T + 1, dtype=float), a=1 / sod ** 2, scale=mod * sod ** 2)
-        cols = {"sim": g["sim"].to_numpy(), "time": g["time"].to_numpy()}
-        if by_chain:
-            cols = {"chain": g["chain"].to_numpy(), **cols}
-        for nm in m.IFRparams:
-            cols[nm] = g[nm].to_numpy()
-            cols["deaths_" + nm] = np.convolve(g["infxns_" + nm].to_numpy() * float(g[nm].iloc[0]), kern)[:T]
-        frames.append(pd.DataFrame(cols))
-    return pd.concat(frames, ignore_index=True)
+    deaths[j][a] = sum_{i <= j} infxns[i][a] * ifr[a] * dgamma(j - i; 1/sod^2, mod sod^2)  (the DENSITY, :605-641),
+    evaluated on the device for all draws at once (cc_post_deaths_batch).  One row per (draw, day) with the draw's IFR
+    columns and `deaths_<stratum>`."""
+    from . import _lib
+    nodes = _downsample(IFRmodel_inf, whichrung, dwnsmpl, seed)
+    inp = IFRmodel_inf["inputs"]
+    m = inp["IFRmodel"]
+    spec = build_spec(m, inp["binomial_likelihood"], False, False, False)
+    model = _lib.Model(spec, device=device)
+    try:
+        deaths = model.post_deaths(nodes[spec.names].to_numpy(dtype=np.float64))          # [draw][day][stratum]
+    finally:
+        model.close()
+    n, T = len(nodes), spec.T
+    cols = {"sim": np.repeat(_sim_index(nodes, by_chain), T), "time": np.tile(np.arange(1, T + 1), n)}
+    if by_chain:
+        cols = {"chain": np.repeat(nodes["chain"].to_numpy(), T), **cols}
+    for a, nm in enumerate(m.IFRparams):
+        cols[nm] = np.repeat(nodes[nm].to_numpy(), T)
+    for a, nm in enumerate(m.IFRparams):
+        cols["deaths_" + nm] = deaths[:, :, a].reshape(-1)
+    return pd.DataFrame(cols)

@@ -180,15 +180,25 @@ def get_cred_intervals(IFRmodel_inf, what: str, whichrung: str | None = None, by
     return pd.DataFrame(rows)
 
 
-def get_overall_IFR_cred_intervals(IFRmodel_inf, whichrung: str | None = None, by_chain: bool = True) -> pd.DataFrame:
-    """R/summarize_plot.R:162-264: overall IFR per draw = sum_a ma_a * w_a with w = demography weights re-weighted by the
-    attack-rate (noise) parameters, then the same summary columns as get_cred_intervals."""
+def overall_ifr_weights(m, whichstandard: str):
+    """(popN, use_noise) of R/summarize_plot.R:162-264: "pop" weights by demography alone, "arpop" by attack rate x demography."""
+    if whichstandard not in ("pop", "arpop"):
+        raise ValueError("Standardization must either be by populatin (pop) or by population and attack rate (arpop)")
+    if whichstandard == "arpop" and not m.Noiseparams:
+        raise ValueError("arpop needs the attack-rate (noise) parameters")
+    return m.demog["popN"].to_numpy(dtype=float), whichstandard == "arpop"
+
+
+def get_overall_IFR_cred_intervals(IFRmodel_inf, whichstandard: str = "pop", whichrung: str | None = None, by_chain: bool = True) -> pd.DataFrame:
+    """R/summarize_plot.R:162-264: overall IFR per draw = sum_a ma_a * w_a with w = popN / sum(popN) (whichstandard = "pop", the
+    reference's default) or the attack-rate re-weighted demography ("arpop"), then the summary columns of get_cred_intervals."""
+    from scipy import stats
     m = IFRmodel_inf["inputs"]["IFRmodel"]
+    pop, use_noise = overall_ifr_weights(m, whichstandard)
     rung = whichrung or default_cold_rung(IFRmodel_inf)
     df = _sampling_rows(IFRmodel_inf, rung)
-    pop = m.demog["popN"].to_numpy(dtype=float)
     ma = df[m.IFRparams].to_numpy(dtype=float)
-    ne = df[m.Noiseparams].to_numpy(dtype=float) if m.Noiseparams else np.ones_like(ma)
+    ne = df[m.Noiseparams].to_numpy(dtype=float) if use_noise else np.ones_like(ma)
     w = ne * pop[None, :]
     w = w / w.sum(axis=1, keepdims=True)
     overall = (ma * w).sum(axis=1)
@@ -197,9 +207,66 @@ def get_overall_IFR_cred_intervals(IFRmodel_inf, whichrung: str | None = None, b
     for ch in keys:
         x = overall if ch is None else overall[(df["chain"] == ch).to_numpy()]
         q = np.quantile(x, [0.025, 0.5, 0.975])
-        row = dict(param="overall_IFR", min=x.min(), LCI=q[0], median=q[1], mean=x.mean(), UCI=q[2], max=x.max(), ESS=effective_size(x),
-                   GewekeZ=geweke_z(x))
+        z = geweke_z(x)
+        row = dict(min=x.min(), LCI=q[0], median=q[1], mean=x.mean(), UCI=q[2], max=x.max(), ESS=effective_size(x),
+                   GewekeZ=z, GewekeP=float(stats.norm.pdf(z)))
         if ch is not None:
             row = dict(chain=ch, **row)
         rows.append(row)
     return pd.DataFrame(rows)
+
+
+# ------------------------------------------------------------------------------------- the same summaries on the device
+# (covidcurve_b200/csrc/cc_summ.cu through the C ABI).  `draws` is [chains, iterations, params]: a numpy array (uploaded) or a
+# CUDA torch tensor (used where it lives - the recorded draws of a run, or the NCCL all-gathered tensor of dist.allgather_draws).
+_COLS = ("min", "LCI", "median", "mean", "UCI", "max", "ESS", "GewekeZ", "GewekeP")
+
+
+def device_cred_intervals(draws, names, by_chain: bool = True, chain_ids=None, device: int = 0) -> pd.DataFrame:
+    """get_cred_intervals' table (R/summarize_plot.R:136-152) for every parameter in `names` (the last axis of `draws`)."""
+    from . import _lib
+    tab = _lib.summarize_draws(draws, by_chain=by_chain, device=device)                  # [groups, params, fields]
+    G, P = tab.shape[:2]
+    if len(names) != P:
+        raise ValueError("names must label the last axis of draws")
+    cols = {}
+    if by_chain:
+        ids = np.arange(1, G + 1) if chain_ids is None else np.asarray(chain_ids)
+        cols["chain"] = np.repeat(ids, P)
+    cols["param"] = np.tile(np.asarray(names, dtype=object), G)
+    for f, c in enumerate(_COLS):
+        cols[c] = tab[:, :, f].reshape(-1)
+    return pd.DataFrame(cols)
+
+
+def device_gelman_diag(draws, confidence: float = 0.95, autoburnin: bool = True, device: int = 0):
+    """coda::gelman.diag(transform = FALSE, multivariate = FALSE) from device-side moments: (point estimate, upper limit, drjacoby
+    rhat) per parameter.  Only the F quantile of the upper limit (one scalar per parameter) is taken on the host."""
+    from . import _lib
+    n = draws.shape[1]
+    first = n // 2 if autoburnin else 0                      # coda: window(x, start = end/2 + 1)
+    mean, var = _lib.chain_moments(draws, first_iter=first, device=device)
+    return gelman_from_chain_moments(mean, var, n - first, confidence, device)
+
+
+def gelman_from_chain_moments(mean, var, n_used: int, confidence: float = 0.95, device: int = 0):
+    from scipy import stats
+    from . import _lib
+    g = _lib.gelman_from_moments(mean, var, n_used, device=device)
+    C = mean.shape[0]
+    f = dict(zip(_lib.GELMAN_FIELDS, g.T))
+    upper = np.sqrt(f["df_adj"] * (f["R2_fixed"] + stats.f.ppf((1 + confidence) / 2, C - 1, f["W_df"]) * f["R2_random"]))
+    return f["psrf"], upper, f["rhat"]
+
+
+def device_overall_IFR_cred_intervals(draws, names, IFRparams, popN, Noiseparams=None, by_chain: bool = True, device: int = 0) -> pd.DataFrame:
+    """get_overall_IFR_cred_intervals on the device: the per-draw overall IFR (cc_overall_ifr_draws) summarised like a parameter.
+    Noiseparams = None is the reference's default standard ("pop"), a list of names "arpop"."""
+    from . import _lib
+    names = list(names)
+    idx_ifr = [names.index(p) for p in IFRparams]
+    idx_noise = None if Noiseparams is None else [names.index(p) for p in Noiseparams]
+    est = _lib.overall_ifr_draws(draws, idx_ifr, popN, idx_noise, device=device)
+    est3 = est[:, :, None]
+    out = device_cred_intervals(est3, ["overall_IFR"], by_chain=by_chain, device=device)
+    return out.drop(columns=["param"])

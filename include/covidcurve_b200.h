@@ -174,6 +174,50 @@ int cc_loglike_call(const cc_call_args* args, const double* params, int param_i,
 int cc_curves_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* infxn, double* ne, double* auc,
                     double* sero_full);
 
+/*
+ * Posterior check of expected deaths (posterior_check_infxns_to_death, R/summarize_plot.R:591-680; the compiled loop at
+ * :605-641): per parameter vector (draw) and stratum
+ *     deaths[j][a] = sum_{i <= j} (ne[a] * infxn[i]) * ifr[a] * dgamma(j - i; shape = 1/sod^2, scale = mod * sod^2)
+ * with the gamma DENSITY (R::dgamma) as the delay kernel, terms added in the reference's order (i = 0, 1, ...), each product
+ * rounded.  theta: host, SoA like cc_loglike_batch, the stored (already lifted) posterior values; deaths: host [n][T][A].
+ * A draw whose knots are not increasing has no curve: its block is NaN.
+ */
+int cc_post_deaths_batch(cc_model* m, const double* theta, int64_t n, int64_t ld, double* deaths);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Posterior summaries of recorded draws ON THE DEVICE (the consumers of the fit object: R/summarize_plot.R:46-58
+ * get_gelman_rubin_diagnostic -> coda::gelman.diag, :68-153 get_cred_intervals, :162-264 get_overall_IFR_cred_intervals).
+ * `draws` holds element (chain c, iteration i, parameter p) at draws[c * stride_chain + i * stride_iter + p]  (doubles);
+ * with mem = CC_MEM_DEVICE it is a device pointer (cc_mcmc_device_draws, or an NCCL all-gathered tensor) and `stream`
+ * orders the work after whatever produced it; with CC_MEM_HOST the draws are uploaded first.  Outputs marked HOST are
+ * always host arrays (they are small); every call returns after its results are complete.
+ * --------------------------------------------------------------------------------------------------------- */
+#define CC_SUMM_FIELDS 12
+/* fields: 0 min, 1 LCI (2.5 %, type-7 quantile), 2 median, 3 mean, 4 UCI (97.5 %), 5 max, 6 ESS (coda::effectiveSize),
+   7 GewekeZ (coda::geweke.diag, frac1 = 0.1, frac2 = 0.5), 8 GewekeP = dnorm(GewekeZ), 9 variance (n - 1), 10 spectral density at
+   zero (coda::spectrum0.ar), 11 series length.
+   by_chain != 0: one row per (chain, parameter), out HOST [n_chains][n_params][CC_SUMM_FIELDS];
+   by_chain == 0: the chains' series concatenated in chain order (dplyr::group_by(param)), out HOST [1][n_params][CC_SUMM_FIELDS]. */
+int cc_summarize_draws(int device, const double* draws, int64_t n_chains, int64_t n_iter, int32_t n_params,
+                       int64_t stride_chain, int64_t stride_iter, int32_t by_chain, int mem, void* stream, double* out);
+/* per-chain mean and unbiased variance of iterations [first_iter, n_iter): mean, var [n_chains][n_params], in the memory
+   space `mem` names (device arrays can be all-gathered over the ranks before cc_gelman_from_moments) */
+int cc_chain_moments(int device, const double* draws, int64_t n_chains, int64_t n_iter, int32_t n_params, int64_t stride_chain,
+                     int64_t stride_iter, int64_t first_iter, int mem, void* stream, double* mean, double* var);
+#define CC_GELMAN_FIELDS 8
+/* from per-chain moments of n_iter_used draws each: out HOST [n_params][CC_GELMAN_FIELDS] =
+   0 drjacoby's rhat (sqrt(((1 - 1/n) W + B/n) / W)), 1 coda::gelman.diag point estimate (transform = FALSE, with the
+   degrees-of-freedom correction), 2 W, 3 B, 4 df of W, 5 df adjustment, 6 fixed and 7 random part of R^2: coda's upper limit is
+   sqrt(f5 * (f6 + qf((1 + confidence) / 2, n_chains - 1, f4) * f7)) - one F quantile per parameter, left to the host */
+int cc_gelman_from_moments(int device, const double* mean, const double* var, int64_t n_chains, int64_t n_iter_used,
+                           int32_t n_params, int mem, void* stream, double* out);
+/* overall IFR per draw (R/summarize_plot.R:162-264): est[c][i] = sum_a draws[.., idx_ifr[a]] * w_a with w_a = popN_a / sum popN
+   (idx_noise == NULL: whichstandard = "pop") or noise_a popN_a / sum_b noise_b popN_b ("arpop"); est [n_chains][n_iter] in the
+   memory space `mem` names - summarise it with cc_summarize_draws(n_params = 1) */
+int cc_overall_ifr_draws(int device, const double* draws, int64_t n_chains, int64_t n_iter, int32_t n_params, int64_t stride_chain,
+                         int64_t stride_iter, const int32_t* idx_ifr, const int32_t* idx_noise, const double* popN, int32_t n_strata,
+                         int mem, void* stream, double* est);
+
 /* ---------------------------------------------------------------------------------------------------------
  * GPU-resident Metropolis-coupled MCMC replacing drjacoby::run_mcmc (call site R/main.R:179-193).
  * One particle per (chain, rung); single-site Metropolis-Hastings sweep over the d parameters with

@@ -386,3 +386,26 @@ extern "C" void cco_logprior_many(const cco_desc* m, const double* params, long 
     for (long r = lo; r < hi; r++) out[r] = cco_logprior(m, params + r * m->d, 1);
   });
 }
+
+/* get_post_deaths of posterior_check_infxns_to_death (R/summarize_plot.R:605-641), loop for loop: `infxns` is the
+   unlisted data frame of the per-stratum infection curves (column after column: stratum-major), the delay kernel is the
+   gamma DENSITY at integer lags, out[day][stratum] += infxns[i][a] * ifr[a] * gmmlkup[delta]. */
+extern "C" void cco_post_deaths(const double* infxns, const double* ifr, int daylen, int stratlen, double mod, double sod, double* out) {
+  std::vector<double> gmmlkup(daylen + 1);
+  for (int i = 0; i < (daylen + 1); i++) gmmlkup[i] = cco_dgamma(i, 1 / std::pow(sod, 2), mod * std::pow(sod, 2), 0);
+  std::vector<std::vector<double>> infxns_strata(daylen, std::vector<double>(stratlen));
+  int iter = 0;
+  for (int j = 0; j < stratlen; j++)
+    for (int i = 0; i < daylen; i++) {
+      infxns_strata[i][j] = infxns[iter];
+      iter++;
+    }
+  std::vector<std::vector<double>> exp_death_day_strata(daylen, std::vector<double>(stratlen, 0.0));
+  for (int i = 0; i < daylen; i++)
+    for (int j = i + 1; j < (daylen + 1); j++) {
+      int delta = j - i - 1;
+      for (int a = 0; a < stratlen; a++) exp_death_day_strata[j - 1][a] += infxns_strata[i][a] * ifr[a] * gmmlkup[delta];
+    }
+  for (int i = 0; i < daylen; i++)
+    for (int a = 0; a < stratlen; a++) out[(long)i * stratlen + a] = exp_death_day_strata[i][a];
+}

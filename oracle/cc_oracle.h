@@ -83,6 +83,9 @@ double cco_logprior(const cco_desc* m, const double* params, int param_i);
 void cco_loglike_many(const cco_desc* m, const double* params, long n, double* out, int nthreads);
 void cco_logprior_many(const cco_desc* m, const double* params, long n, double* out, int nthreads);
 
+/* get_post_deaths (R/summarize_plot.R:605-641): infxns [stratlen][daylen] (stratum-major, as R unlists the data frame), out [daylen][stratlen] */
+void cco_post_deaths(const double* infxns, const double* ifr, int daylen, int stratlen, double mod, double sod, double* out);
+
 /* drjacoby-equivalent MCMC (see cc_oracle_mcmc.cpp) */
 typedef struct cco_mcmc_opts {
   int burnin, samples, rungs, chains;

@@ -84,6 +84,8 @@ def lib():
             getattr(L, name).argtypes = [C.POINTER(_Desc), c_dp, C.c_long, c_dp, C.c_int]
         L.cco_mcmc.restype = C.c_int
         L.cco_mcmc.argtypes = [C.POINTER(_Desc), c_dp, C.POINTER(_McmcOpts), c_dp, c_dp, c_dp, c_dp, c_dp]
+        L.cco_post_deaths.restype = None
+        L.cco_post_deaths.argtypes = [c_dp, c_dp, C.c_int, C.c_int, dbl, dbl, c_dp]
         L.cco_philox_kat.restype = C.c_int
         L.cco_philox_kat.argtypes = [C.POINTER(C.c_uint)] * 3
         L.cco_draw.restype = None
@@ -157,6 +159,19 @@ class Oracle:
         ll = self.L.cco_loglike(C.byref(self.desc), _dp(th), 1, C.byref(tr))
         bufs.update(loglike=ll, L1=tr.L1, L2=tr.L2, L3=tr.L3, status=tr.status)
         return bufs
+
+    def post_deaths(self, theta):
+        """Expected deaths [T][A] of one posterior draw (R/summarize_plot.R:591-680): per-stratum infection curves ne[a] * infxn[t]
+        from the oracle's own evaluation, then the reference's get_post_deaths loop.  `theta` holds stored (lifted) values."""
+        s = self.spec
+        assert not (s.reparamIFR or s.reparamKnots or s.reparamInfxn), "posterior draws are stored un-reparameterised"
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1))
+        tr = self.trace(th)
+        strata = np.ascontiguousarray((tr["ne"][:, None] * tr["infxn"][None, :]))           # [A][T]: stratum-major like unlist()
+        ifr = np.ascontiguousarray([th[s.index(nm)] for nm in s.IFRparams])
+        out = np.empty((s.T, s.A))
+        self.L.cco_post_deaths(_dp(strata), _dp(ifr), s.T, s.A, float(th[s.index(s.modparam)]), float(th[s.index(s.sodparam)]), _dp(out))
+        return out
 
     def mcmc(self, burnin, samples, rungs=1, chains=1, coupling_on=True, GTI_pow=1.0, beta_manual=None, seed=1,
              nthreads=1, cold_rung_last=True, init=None, chain_offset=0):
