@@ -19,11 +19,13 @@ cap() {  # name, kernel regex, skip, mangled substring, command
   "$@" > $O/${TAG}_plain_$name.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -o /tmp/$name "$@" > $O/${TAG}_ncu_$name.log 2>&1
   ncu -i /tmp/$name.ncu-rep --page details > $O/${TAG}_${name}_details.txt 2>/dev/null
   ncu -i /tmp/$name.ncu-rep --page raw --csv > $O/${TAG}_${name}_raw.csv 2>/dev/null
+  python tools/ncu_metrics.py $O/${TAG}_${name}_raw.csv > $O/${TAG}_${name}_metrics.txt 2>&1
   NCU_LINES_OUTER=1 python tools/ncu_lines.py /tmp/$name.ncu-rep $LIB $sym 40 > $O/${TAG}_${name}_stages.txt 2>&1
   python tools/ncu_lines.py /tmp/$name.ncu-rep $LIB $sym 90 > $O/${TAG}_${name}_lines.txt 2>&1
   rm -f /tmp/$name.ncu-rep
 }
 cap phase2_box loglike_phase2 3 loglike_phase2_kernelILi5 python tools/ll_once.py box 262144 5
+python tools/traffic_json.py $O/${TAG}_phase2_box_raw.csv 262144 $O/${TAG}_traffic.json > /dev/null 2>&1
 cap phase2_post loglike_phase2 3 loglike_phase2_kernelILi5 python tools/ll_once.py post 262144 5
 cap mcmc_sweep mcmc_sweep 104 mcmc_sweep_cached_kernelILi5 python tools/mcmc_bench.py --cfgs cfg3
 ls -la $O | grep ${TAG}_ | tail -40
