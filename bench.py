@@ -488,9 +488,48 @@ def main():
                                "bytes": 3 * spec4.d * 8, "ms": float(np.median(ar_ms))},
             "rhat_max_abs_diff_allreduce_vs_gathered": float((rh_red - rh_gat).abs().max().item()),
             "rhat_median": float(rh_gat.median().item()), "timing": "CUDA events, median of %d, max over ranks" % reps}
+        # ---- posterior summaries ON THE DEVICE next to the gathered draws (csrc/cc_summ.cu; R/summarize_plot.R:46-153):
+        # (a) coda::gelman.diag + drjacoby R-hat without moving a draw: per-chain moments by the library's kernel, an NCCL
+        #     all-gather of 2 x chains x d numbers, the finishing kernel; (b) the credible-interval table pooled over all 4096
+        #     chains from the gathered tensor (radix-select quantiles, AR spectrum -> ESS / Geweke); (c) the same per chain,
+        #     every rank summarising its own chains, only the rows travelling
+        from covidcurve_b200 import summaries as ccsum
+        def timed_ms(fn, reps=3):
+            ts = []
+            for _ in range(reps):
+                barrier()
+                t0 = time.perf_counter()
+                r = fn()
+                torch.cuda.synchronize()
+                ts.append(reduce_ranks((time.perf_counter() - t0) * 1e3))
+            return r, float(np.median(ts))
+        for _ in range(2):                                                                    # warm-up (imports, NCCL set-up)
+            ccdist.gelman_allgather(draws, chains4)
+        (psrf, psrf_up, rh_k), ms_gel = timed_ms(lambda: ccdist.gelman_allgather(draws, chains4))
+        pooled, ms_pool = timed_ms(lambda: _lib.summarize_draws(gathered, by_chain=False))
+        bychain, ms_chain = timed_ms(lambda: ccdist.cred_intervals_allgather(draws, chains4, spec4.names))
+        collective["device_summaries"] = {
+            "gelman_allgather": {"what": "cc_chain_moments on local draws -> all-gather of [chains, 2, d] moments -> cc_gelman_from_moments",
+                                 "bytes_gathered": 2 * chains4 * spec4.d * 8, "ms": ms_gel, "psrf_median": float(np.median(psrf)),
+                                 "psrf_upper_median": float(np.median(psrf_up))},
+            "pooled_table": {"what": "cc_summarize_draws(by_chain=0) on the gathered tensor: %d series of %d draws" % (spec4.d, chains4 * it4),
+                             "ms": ms_pool},
+            "by_chain_table": {"what": "cc_summarize_draws(by_chain=1) per rank on its own chains + all-gather of the rows",
+                               "rows": int(len(bychain)), "ms": ms_chain},
+            "timing": "host wall clock around the call incl. synchronisation, max over ranks, median of 3"}
         if rank == 0:
             from covidcurve_b200.summaries import rhat_per_parameter
-            host = rhat_per_parameter(gathered.cpu().numpy())
+            gat = gathered.cpu().numpy()
+            half = gat[:, it4 // 2:, :]
+            e_host, u_host = ccsum.gelman_diag(gat)
+            q_host = np.quantile(gat.reshape(-1, spec4.d), [0.025, 0.5, 0.975], axis=0).T
+            ds = collective["device_summaries"]
+            ds["gelman_allgather"]["max_rel_diff_vs_host_numpy"] = float(np.nanmax(np.abs(psrf - e_host) / e_host))
+            ds["gelman_allgather"]["rhat_max_abs_diff_vs_host_numpy"] = float(np.nanmax(np.abs(rh_k - rhat_per_parameter(half))))
+            ds["pooled_table"]["quantiles_equal_numpy"] = bool(np.array_equal(pooled[0][:, [1, 2, 4]], q_host))
+            ds["by_chain_table"]["medians_equal_numpy"] = bool(np.array_equal(
+                bychain["median"].to_numpy().reshape(chains4, spec4.d), np.quantile(gat, 0.5, axis=1)))
+            host = rhat_per_parameter(gat)
             collective["rhat_max_abs_diff_device_vs_host_numpy"] = float(np.max(np.abs(host - rh_gat.cpu().numpy())))
             # the gathered block of rank 0's own chains is bit for bit what rank 0 recorded
             collective["gathered_equals_local"] = bool(np.array_equal(gathered[:c_loc].cpu().numpy(), out4["theta"][:, 0, rows - it4:rows, :]))
