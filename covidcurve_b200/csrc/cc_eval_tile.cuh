@@ -13,6 +13,9 @@
 // Stage map and reference line numbers: see cc_eval_warp.cuh / SURVEY.md 3.2.
 #pragma once
 #include "cc_eval_warp.cuh"
+#ifndef CC_P2_EXPERIMENT
+#define CC_P2_EXPERIMENT 0
+#endif
 
 namespace ccdev {
 
@@ -24,10 +27,10 @@ struct RecLayout {
 __host__ __device__ inline RecLayout rec_layout(int K, int A, int S) {
   RecLayout L;
   L.flags = 0;            // 1 = knots ordered
-  L.gam = 1;              // alph, scale, h, lgam_a, lsc, km, nser, QT, fast, lgam_a1, logA, exp(-h), k_hi
-  L.sero = 14;            // rate, g1, g32, fac | rate, shape, lws, badw
-  L.snm = 18;
-  L.ne = 19;              // [A]
+  L.gam = 1;              // alph, scale, h, lgam_a, lsc, km, nser, QT, fast, lgam_a1, logA, exp(-h), k_hi, sigma_top
+  L.sero = 15;            // rate, g1, g32, fac | rate, shape, lws, badw
+  L.snm = 19;
+  L.ne = 20;              // [A]
   L.spl = L.ne + A;       // per interval j < K-1: x_j, y_j, sp1_j, sp2_j, sp3_j
   L.cday = L.spl + 5 * (K - 1);  // cday[1..K-2]
   L.n2 = L.cday + (K - 2);
@@ -208,6 +211,9 @@ __device__ inline bool p1_spline(const KModel& m, const RecLayout& L, Par par, P
   return true;
 }
 
+// number of interval-mass coefficients: the scaled coefficients c'_m = c_m / x_{km+1}^m decay like P(m+1, h)
+__device__ __forceinline__ int gamma_ncoef(double h) { return (h <= 3.6) ? 32 : (h <= 16.0) ? 64 : (h <= 32.0) ? 96 : 128; }
+
 // delay-kernel constants (scheme: tile_gamma below)
 template <int NT, typename Par, typename Put>
 __device__ inline void p1_gamma(const KModel& m, const RecLayout& L, Par par, Put put) {
@@ -266,6 +272,19 @@ __device__ inline void p1_gamma(const KModel& m, const RecLayout& L, Par par, Pu
     k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;  // masses beyond this day are < 2^-54 of the total: exactly zero
   }
   put(L.gam + 9, lgam_a1); put(L.gam + 10, logA); put(L.gam + 11, emh); put(L.gam + 12, k_hi);
+  // top of the sigma recurrence of the interval-mass coefficients (tile_gamma): ONE short series at m = nct (ratio
+  // h / (nct + j) <= 3/8) - serial work, so it belongs to the thread-per-vector pass, not to every lane of a warp
+  double sig_top = 0.0;
+  if (fast && km < T) {
+    const int nct = gamma_ncoef(h);
+    double term = m.rk[nct + 1], sum = term;
+    for (int j = 1; j < 200 && term > 1e-18 * sum; j++) {
+      term *= h * m.rk[nct + 1 + j];
+      sum += term;
+    }
+    sig_top = sum;
+  }
+  put(L.gam + 13, sig_top);
 }
 
 // sero constants (binomial.cpp:257-284)
@@ -310,24 +329,15 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
   double* ctab = w.ctab;
   const double kLogTol = 36.5;  // interval-mass series truncated below e^-36.5 = 1.4e-16 of the leading term
 
-  // number of interval-mass coefficients: the scaled coefficients c'_m = c_m / x_{km+1}^m decay like P(m+1, h)
-  const int nct = (h <= 3.6) ? 32 : (h <= 16.0) ? 64 : (h <= 32.0) ? 96 : 128;
+  const int nct = gamma_ncoef(h);
   if (fast && km < T) {
     // c'_m = binom(a-1, m) (km+1)^-m * h e^-h sigma_m,  sigma_m = sum_j h^j / ((m+1)...(m+1+j));  lane holds m = lane + 32 g.
-    // sigma obeys sigma_m = (1 + h sigma_{m+1}) / (m+1): ONE short series at m = nct (ratio h / (nct + j) <= 3/8), then the
+    // sigma obeys sigma_m = (1 + h sigma_{m+1}) / (m+1): ONE short series at m = nct (p1_gamma: record field gam + 13), then the
     // recurrence downwards as a warp scan over affine maps, 32 values per round (errors shrink going down).  A series per
     // lane - up to 100 rounds of a dependent multiply-add for every group at large h - was 8 % of the box workload.
     const double emh = w.rec[L.gam + 11], rk1 = tb.rk[km + 1];
     const int ng = nct >> 5;
-    double sig_next;
-    {
-      double term = m.rk[nct + 1], sum = term;
-      for (int j = 1; j < 200 && term > 1e-18 * sum; j++) {
-        term *= h * m.rk[nct + 1 + j];
-        sum += term;
-      }
-      sig_next = sum;
-    }
+    double sig_next = w.rec[L.gam + 13];
     double sig[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int g = 3; g >= 0; g--) {
@@ -784,8 +794,18 @@ __device__ inline void tile_phase2(const KModel& m, const RecLayout& L, const Ti
   __syncwarp();
   if (w.rec[L.flags] == 0.0) return;  // knots not increasing: phase 3 returns the failure value
 
+#if CC_P2_EXPERIMENT == 2  // timing experiment (results invalid): the delay kernel alone
+  tile_gamma<NT>(m, L, w, tb);
+  if (lane == 0) scr[L.o_l1 * stride + e] = w.gs[7 + 5] + w.gs[7 + T - 1];
+  return;
+#endif
   tile_sero_prefix<NT>(m, L, w, tb);   // S10 (first: with seroreversion it borrows the series/kernel regions)
+#if CC_P2_EXPERIMENT == 1  // timing experiment (results invalid): everything but the delay kernel
+  for (int k = lane; k < 64 * NT + 9; k += 32) w.gs[7 + k] = (k < T) ? 1.0 / (double)T : 0.0;
+  __syncwarp();
+#else
   tile_gamma<NT>(m, L, w, tb);         // S2
+#endif
   const double tot = stage_spline<NT>(m, L, w.rec, w.xs);
   const bool ok = stage_popn(m, L, w.rec, tot);
   if (lane == 0) scr[L.o_status * stride + e] = ok ? 0.0 : 1.0;

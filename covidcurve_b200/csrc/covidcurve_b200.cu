@@ -104,7 +104,10 @@ constexpr int kSweepWarps = CC_SWEEP_WARPS;
 // pass D (one THREAD per vector): phase 3.
 // Grouping by regime keeps the warps of a CTA on the same code path (small gamma table / large table / general algorithm /
 // no per-day work at all) and lets the launch start with the expensive vectors (history: profiles/r1_summary.md).
-constexpr int kNumKeys = 8;       // histogram slots; keys 0..5 are used, slot 6 is the phase-2 tile ticket
+constexpr int kNumKeys = 8;       // histogram slots: key 0 = no per-day work, 1 .. 4 = size of the gamma coefficient table, 7 = general
+                                  // incomplete-gamma algorithm; the phase-2 tile ticket lives behind the two arrays.  (Ordering the
+                                  // vectors by an estimated cost of the per-day pass in 126 buckets instead - so that the warps of a
+                                  // CTA also FINISH every evaluation together - measured slower: 88.4 vs 92.0 M evals/s, round 2.)
 constexpr int kLoglikeLaunches = 5;  // kernels per cc_loglike_batch pipeline (launch_loglike)
 #ifndef CC_P2_TILE
 #define CC_P2_TILE 2
@@ -127,40 +130,36 @@ __global__ void __launch_bounds__(128) loglike_phase1_kernel(const KModel m, con
     if (p1_spline(m, L, par, put)) {
       p1_gamma<NT>(m, L, par, put);
       p1_sero(m, L, par, put);
-      const double fast = rec[(long long)(L.gam + 8) * cap + v], h = rec[(long long)(L.gam + 2) * cap + v];
-      k = (fast == 0.0) ? 5 : (h <= 3.6) ? 1 : (h <= 16.0) ? 2 : (h <= 32.0) ? 3 : 4;
+      const double fast = rec[(long long)(L.gam + 8) * cap + v];
+      const double h = rec[(long long)(L.gam + 2) * cap + v];
+      k = (fast == 0.0) ? (kNumKeys - 1) : (h <= 3.6) ? 1 : (h <= 16.0) ? 2 : (h <= 32.0) ? 3 : 4;
     }
     key[v] = k;
   }
   // warp-aggregated histogram
-  for (int q = 0; q < 6; q++) {
-    const unsigned mask = __ballot_sync(0xffffffffu, k == q);
-    if (mask && (threadIdx.x & 31) == (__ffs(mask) - 1)) atomicAdd(&counts[q], (unsigned)__popc(mask));
-  }
+  const unsigned peers = __match_any_sync(0xffffffffu, k);
+  if (k >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&counts[k], (unsigned)__popc(peers));
 }
 
 __global__ void bucket_offsets_kernel(const unsigned int* __restrict__ counts, unsigned int* __restrict__ cursor) {
-  // heavy regimes first, so that the long-running tiles start early and the tail of the launch is made of cheap ones
-  const int order[6] = {5, 4, 3, 2, 1, 0};
+  // heavy vectors first, so that the long-running tiles start early and the tail of the launch is made of cheap ones
   unsigned int run = 0;
-  for (int q = 0; q < 6; q++) {
-    cursor[order[q]] = run;
-    run += counts[order[q]];
+  for (int q = kNumKeys - 1; q >= 0; q--) {
+    cursor[q] = run;
+    run += counts[q];
   }
 }
 
 __global__ void bucket_scatter_kernel(const int* __restrict__ key, long long n, unsigned int* __restrict__ cursor, int* __restrict__ perm) {
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = (v < n) ? key[v] : -1;
-  for (int q = 0; q < 6; q++) {
-    const unsigned mask = __ballot_sync(0xffffffffu, k == q);
-    if (!mask) continue;
-    const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
-    unsigned int base = 0;
-    if (lane == leader) base = atomicAdd(&cursor[q], (unsigned)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (k == q) perm[base + __popc(mask & ((1u << lane) - 1))] = (int)v;
-  }
+  const unsigned peers = __match_any_sync(0xffffffffu, k);
+  if (k < 0) return;
+  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(&cursor[k], (unsigned)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  perm[base + __popc(peers & ((1u << lane) - 1))] = (int)v;
 }
 
 // tile_phase2 with a CTA barrier in front of every stage: all warps of the CTA execute the same stage code at the same
@@ -1110,7 +1109,7 @@ extern "C" void cc_model_destroy(cc_model* m) {
 // ------------------------------------------------------------------------------------------------ batch calls
 static int ensure_work(cc_model* m, int slot, long long n) {
   cc_model::Work& wk = m->work[slot];
-  if (!wk.counts) CC_CUDA(cudaMalloc((void**)&wk.counts, 2 * kNumKeys * sizeof(unsigned int)));
+  if (!wk.counts) CC_CUDA(cudaMalloc((void**)&wk.counts, (2 * kNumKeys + 8) * sizeof(unsigned int)));
   if (wk.cap >= n) return CC_OK;
   if (wk.rec) cudaFree(wk.rec);
   if (wk.key) cudaFree(wk.key);
@@ -1134,7 +1133,7 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
   cc_model::Work& wk = m->work[slot];
   unsigned int* counts = wk.counts;
   unsigned int* cursor = wk.counts + kNumKeys;
-  CC_CUDA(cudaMemsetAsync(counts, 0, 2 * kNumKeys * sizeof(unsigned int), st));
+  CC_CUDA(cudaMemsetAsync(counts, 0, (2 * kNumKeys + 8) * sizeof(unsigned int), st));
   const unsigned gridA = (unsigned)((n + 127) / 128);
   const size_t smem = warp_cta_smem(k, m->nt);
   const long long tiles = (n + kPhase2Tile - 1) / kPhase2Tile;
@@ -1146,7 +1145,7 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
     loglike_phase1_kernel<NT_><<<gridA, 128, 0, st>>>(k, d_theta, n, ld, wk.rec, wk.cap, wk.key, counts);                     \
     bucket_offsets_kernel<<<1, 1, 0, st>>>(counts, cursor);                                                                   \
     bucket_scatter_kernel<<<gridA, 128, 0, st>>>(wk.key, n, cursor, wk.perm);                                                 \
-    loglike_phase2_kernel<NT_><<<gridC, 32 * p2_warps(NT_), smem / kWarpsPerCta * p2_warps(NT_), st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 6, d_theta, ld);                      \
+    loglike_phase2_kernel<NT_><<<gridC, 32 * p2_warps(NT_), smem / kWarpsPerCta * p2_warps(NT_), st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 2 * kNumKeys, d_theta, ld);                      \
     loglike_phase3_kernel<<<gridA, 128, 0, st>>>(k, n, wk.rec, wk.cap, d_out);                                                \
     break;
     CC_FOR_EACH_NT(CC_LAUNCH)
