@@ -3,14 +3,18 @@
 // Built for sm_100a only (see __graft_entry__.build()).  There is no CPU fallback anywhere in this file: every
 // compute entry point needs a CUDA device and returns CC_E_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <string>
@@ -1194,23 +1198,93 @@ static bool host_ptr_is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-// row-wise host copy dst[r * dld + 0..n) <- src[r * sld + 0..n), r < rows, on a few threads (a single thread moves ~10 GB/s,
-// less than the GPU consumes: 272-byte vectors at 80 M evaluations/s are 22 GB/s)
+// A few long-lived helper threads for packing pageable caller memory into the pinned ring (one thread moves ~10 GB/s, the
+// GPU consumes 272-byte vectors at 90 M evaluations/s = 24 GB/s; spawning threads per chunk cost ~10 % of a 128k-vector chunk).
+class CopyPool {
+ public:
+  static CopyPool& get() {
+    static CopyPool p;
+    return p;
+  }
+  int size() const { return (int)th_.size() + 1; }
+  // run job(t) for t = 0 .. n-1 (n <= size()); job 0 on the calling thread
+  void run(int n, const std::function<void(int)>& job) {
+    if (n <= 1 || getpid() != pid_) {  // (a forked child has no helper threads: the caller drains the work queue alone)
+      job(0);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      job_ = &job;
+      njobs_ = n;
+      pending_ = n - 1;
+      gen_++;
+    }
+    cv_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> g(mu_);
+    done_.wait(g, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  CopyPool() : pid_(getpid()) {
+    unsigned hc = std::thread::hardware_concurrency();
+    int n = (int)std::min(8u, std::max(1u, hc / 2));
+    if (const char* e = std::getenv("CC_COPY_THREADS")) n = std::max(1, std::min(32, std::atoi(e)));
+    for (int t = 1; t < n; t++) th_.emplace_back([this, t] { loop(t); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void loop(int t) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job = nullptr;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        if (t < njobs_) job = job_;
+      }
+      if (job) {
+        (*job)(t);
+        std::lock_guard<std::mutex> g(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* job_ = nullptr;
+  int njobs_ = 0, pending_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+  const pid_t pid_;
+};
+
+// row-wise host copy dst[r * dld + 0..n) <- src[r * sld + 0..n), r < rows, split into (row, column-block) pieces over the pool
 static void host_copy_rows(double* dst, size_t dld, const double* src, size_t sld, size_t n, int rows) {
   const size_t bytes = n * sizeof(double) * (size_t)rows;
-  int nth = (int)std::min<size_t>(4, std::max<size_t>(1, bytes >> 22));
-  nth = std::min(nth, std::max(1, rows));
-  auto work = [&](int t) {
-    for (int r = t; r < rows; r += nth) std::memcpy(dst + (size_t)r * dld, src + (size_t)r * sld, n * sizeof(double));
-  };
-  if (nth == 1) {
-    work(0);
-    return;
-  }
-  std::vector<std::thread> th;
-  for (int t = 1; t < nth; t++) th.emplace_back(work, t);
-  work(0);
-  for (auto& t : th) t.join();
+  CopyPool& pool = CopyPool::get();
+  const int nth = (int)std::min<size_t>((size_t)pool.size(), std::max<size_t>(1, bytes >> 21));
+  const size_t blk = 1 << 15;                                   // doubles per piece (256 kB)
+  const size_t nblk = (n + blk - 1) / blk, pieces = nblk * (size_t)rows;
+  std::atomic<size_t> next{0};
+  pool.run(nth, [&](int) {
+    for (size_t p = next.fetch_add(1); p < pieces; p = next.fetch_add(1)) {
+      const size_t r = p / nblk, c0 = (p - r * nblk) * blk, cn = std::min(blk, n - c0);
+      std::memcpy(dst + r * dld + c0, src + r * sld + c0, cn * sizeof(double));
+    }
+  });
 }
 
 // Host-buffer path: column chunks are copied H2D (d rows of `chunk` doubles), evaluated and copied back, triple-buffered
