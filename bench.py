@@ -342,8 +342,8 @@ def main():
         del d_thw, d_outw, thw
 
     # ---------------------------------------------------------------- posterior-like vectors (truth x (1 + 2% noise)), N = 1 only:
-    # the regime an MCMC actually visits (the box-uniform draws above spend ~1/9 of the vectors in sod < 0.115, where the
-    # gamma table falls back to the general incomplete-gamma algorithm)
+    # the regime an MCMC actually visits (3.3 % of the box-uniform draws above have sod < 0.034, where the gamma table falls
+    # back to the general incomplete-gamma algorithm, and 1 % are deliberately invalid)
     value_post = None
     if world == 1:
         near = synth.random_theta(spec, V, seed=synth.SEED_THETA + 1000, bad_frac=0.0, near_truth=synth.true_theta(spec, truth), jitter=0.02)

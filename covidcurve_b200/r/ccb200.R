@@ -112,3 +112,42 @@ ccb200_read_fit <- function(path) {
   fit$inputs$IFRmodel <- m
   fit
 }
+
+# Device-side replacements of the summary functions (R/summarize_plot.R:46-58, 68-153): same arguments, same columns.
+# The sampling rows of one rung are reshaped to the c(n_params, n_iter, n_chains) array the library reads in place.
+ccb200_draws_array <- function(IFRmodel_inf, params, whichrung = "rung1", sampling_only = TRUE) {
+  out <- IFRmodel_inf$mcmcout$output
+  out <- out[out$rung == whichrung & (!sampling_only | out$stage == "sampling"), ]
+  chains <- unique(out$chain)
+  n <- nrow(out) / length(chains)
+  arr <- vapply(chains, function(ch) t(as.matrix(out[out$chain == ch, params, drop = FALSE])), matrix(0, length(params), n))
+  list(draws = array(arr, dim = c(length(params), n, length(chains))), chains = chains)
+}
+
+ccb200_get_cred_intervals <- function(IFRmodel_inf, what, whichrung = "rung1", by_chain = TRUE, device = 0L) {
+  m <- IFRmodel_inf$inputs$IFRmodel
+  params <- switch(what, IFRparams = m$IFRparams, Knotparams = m$Knotparams, Infxnparams = m$Infxnparams,
+                   Serotestparams = m$Serotestparams, Noiseparams = m$Noiseparams, DeathDelayparams = c("mod", "sod"),
+                   stop("what must be one of IFRparams, Knotparams, Infxnparams, Serotestparams, Noiseparams, DeathDelayparams"))
+  d <- ccb200_draws_array(IFRmodel_inf, params, whichrung)
+  tab <- .Call("CCB_summarize_draws", d$draws, as.logical(by_chain), as.integer(device), PACKAGE = "ccb200")
+  groups <- if (by_chain) length(d$chains) else 1L
+  tab <- array(tab, dim = c(12L, length(params), groups))
+  ret <- data.frame(param = rep(params, groups), min = as.numeric(tab[1, , ]), LCI = as.numeric(tab[2, , ]), median = as.numeric(tab[3, , ]),
+                    mean = as.numeric(tab[4, , ]), UCI = as.numeric(tab[5, , ]), max = as.numeric(tab[6, , ]), ESS = as.numeric(tab[7, , ]),
+                    GewekeZ = as.numeric(tab[8, , ]), GewekeP = as.numeric(tab[9, , ]), stringsAsFactors = FALSE)
+  if (by_chain) ret <- cbind(chain = rep(d$chains, each = length(params)), ret)
+  ret
+}
+
+ccb200_get_gelman_rubin_diagnostic <- function(IFRmodel_inf, confidence = 0.95, autoburnin = TRUE, device = 0L) {
+  out <- IFRmodel_inf$mcmcout$output
+  params <- setdiff(names(out), c("chain", "rung", "iteration", "stage", "logprior", "loglikelihood"))
+  chains <- unique(out$chain)                      # like the reference: every row of a chain, no stage or rung filter (:48-51)
+  n <- nrow(out) / length(chains)
+  arr <- vapply(chains, function(ch) t(as.matrix(out[out$chain == ch, params, drop = FALSE])), matrix(0, length(params), n))
+  g <- matrix(.Call("CCB_gelman_draws", array(arr, dim = c(length(params), n, length(chains))), as.logical(autoburnin),
+                    as.integer(device), PACKAGE = "ccb200"), nrow = 8L)
+  upper <- sqrt(g[6, ] * (g[7, ] + stats::qf((1 + confidence) / 2, length(chains) - 1, g[5, ]) * g[8, ]))
+  list(psrf = cbind(`Point est.` = g[2, ], `Upper C.I.` = upper), rhat = stats::setNames(g[1, ], params))
+}

@@ -267,12 +267,62 @@ SEXP CCB_mcmc_run(SEXP model, SEXP opts) {
   return ret;
 }
 
+/*
+ * Posterior summaries on the device (the table of get_cred_intervals / get_overall_IFR_cred_intervals, R/summarize_plot.R:136-152):
+ * `draws` is a numeric array with dim c(n_params, n_iter, n_chains) - aperm() of the sampling rows of one rung - whose column-major
+ * storage is the [chain][iteration][param] layout of cc_summarize_draws.  Returns a CC_SUMM_FIELDS x n_params x groups array
+ * (groups = n_chains when by_chain, else 1): rows min, LCI, median, mean, UCI, max, ESS, GewekeZ, GewekeP, var, spec0, n.
+ */
+SEXP CCB_summarize_draws(SEXP draws, SEXP by_chain, SEXP device) {
+  SEXP dim = Rf_getAttrib(draws, R_DimSymbol);
+  if (Rf_isNull(dim) || Rf_length(dim) != 3) Rf_error("draws must be an array with dim c(n_params, n_iter, n_chains)");
+  const int64_t P = INTEGER(dim)[0], n = INTEGER(dim)[1], C = INTEGER(dim)[2];
+  const int bc = Rf_asLogical(by_chain) ? 1 : 0;
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)CC_SUMM_FIELDS * P * (bc ? C : 1)));
+  if (cc_summarize_draws(as_int(device), REAL(draws), C, n, (int32_t)P, P * n, P, bc, CC_MEM_HOST, NULL, REAL(out)) != CC_OK)
+    ccb_fail("cc_summarize_draws");
+  UNPROTECT(1);
+  return out;
+}
+
+/* coda::gelman.diag ingredients + drjacoby's rhat from the same array: CC_GELMAN_FIELDS x n_params matrix (rows rhat, psrf, W, B,
+   W_df, df_adj, R2_fixed, R2_random); autoburnin = TRUE drops the first half of every chain like coda does */
+SEXP CCB_gelman_draws(SEXP draws, SEXP autoburnin, SEXP device) {
+  SEXP dim = Rf_getAttrib(draws, R_DimSymbol);
+  if (Rf_isNull(dim) || Rf_length(dim) != 3) Rf_error("draws must be an array with dim c(n_params, n_iter, n_chains)");
+  const int64_t P = INTEGER(dim)[0], n = INTEGER(dim)[1], C = INTEGER(dim)[2];
+  const int64_t first = Rf_asLogical(autoburnin) ? n / 2 : 0;
+  double* mean = (double*)R_alloc((size_t)(C * P), sizeof(double));
+  double* var = (double*)R_alloc((size_t)(C * P), sizeof(double));
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)CC_GELMAN_FIELDS * P));
+  if (cc_chain_moments(as_int(device), REAL(draws), C, n, (int32_t)P, P * n, P, first, CC_MEM_HOST, NULL, mean, var) != CC_OK)
+    ccb_fail("cc_chain_moments");
+  if (cc_gelman_from_moments(as_int(device), mean, var, C, n - first, (int32_t)P, CC_MEM_HOST, NULL, REAL(out)) != CC_OK)
+    ccb_fail("cc_gelman_from_moments");
+  UNPROTECT(1);
+  return out;
+}
+
+/* expected deaths of posterior draws with the gamma density kernel (posterior_check_infxns_to_death, R/summarize_plot.R:605-641):
+   theta is an n x d matrix of stored (lifted) draws; returns an n_strata x days x n array */
+SEXP CCB_post_deaths(SEXP model, SEXP theta, SEXP n_strata, SEXP days) {
+  cc_model* m = (cc_model*)R_ExternalPtrAddr(model);
+  const int64_t n = Rf_nrows(theta);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n * as_int(n_strata) * as_int(days)));
+  if (cc_post_deaths_batch(m, REAL(theta), n, n, REAL(out)) != CC_OK) ccb_fail("cc_post_deaths_batch");
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"CCB_model_create", (DL_FUNC)&CCB_model_create, 2},
     {"CCB_loglike", (DL_FUNC)&CCB_loglike, 3},
     {"CCB_loglike_batch", (DL_FUNC)&CCB_loglike_batch, 2},
     {"CCB_logprior_batch", (DL_FUNC)&CCB_logprior_batch, 2},
     {"CCB_mcmc_run", (DL_FUNC)&CCB_mcmc_run, 2},
+    {"CCB_summarize_draws", (DL_FUNC)&CCB_summarize_draws, 3},
+    {"CCB_gelman_draws", (DL_FUNC)&CCB_gelman_draws, 3},
+    {"CCB_post_deaths", (DL_FUNC)&CCB_post_deaths, 4},
     /* the reference's own registration table (src/RcppExports.cpp:37-41): same names, same arity */
     {"_COVIDCurve_natcubspline_loglike_binomial", (DL_FUNC)&_COVIDCurve_natcubspline_loglike_binomial, 4},
     {"_COVIDCurve_natcubspline_loglike_logit", (DL_FUNC)&_COVIDCurve_natcubspline_loglike_logit, 4},

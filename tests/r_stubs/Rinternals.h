@@ -15,7 +15,7 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define REALSXP 14
 #define STRSXP 16
 #define VECSXP 19
-extern SEXP R_NilValue, R_NamesSymbol, R_NaString;
+extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol, R_NaString;
 extern double R_NaReal;
 extern int R_NaInt;
 #define NA_REAL R_NaReal

@@ -10,9 +10,14 @@ rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 50
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-start = next(i for i, l in enumerate(dis) if l.startswith("_Z") and kern in l and l.rstrip().endswith(":"))
+start = None
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):   # one cubin per translation unit of the library
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    start = next((i for i, l in enumerate(dis) if l.startswith("_Z") and kern in l and l.rstrip().endswith(":")), None)
+    if start is not None:
+        break
+if start is None:
+    raise SystemExit("kernel %s not found in %s" % (kern, lib))
 lines = []  # per instruction: attributed (file, line)
 cur = None
 chain = []
