@@ -264,13 +264,17 @@ __device__ inline void p1_gamma(const KModel& m, const RecLayout& L, Par par, Pu
   put(L.gam + 0, alph); put(L.gam + 1, scale); put(L.gam + 2, h); put(L.gam + 3, lgam_a); put(L.gam + 4, lsc);
   put(L.gam + 5, (double)km); put(L.gam + 6, (double)nser); put(L.gam + 7, QT); put(L.gam + 8, fast ? 1.0 : 0.0);
   // per-vector scalars of the per-day pass, computed once here instead of by every lane of the warp there
-  double lgam_a1 = 0.0, logA = 0.0, emh = 0.0, k_hi = 0.0;
+  double lgam_a1 = 0.0, logA = 0.0, emh = 0.0, k_hi = d_inf();
   if (fast) {
     lgam_a1 = lgam_a + log(alph);
     logA = log(fmax(1.0, fabs(alph - 1.0)));
     emh = exp(-h);
-    k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;  // masses beyond this day are < 2^-54 of the total: exactly zero
   }
+  // Beyond x = alph + 9 sqrt(alph) + 45 the upper tail is below 2^-54 (Chernoff: exp(-(t - alph log(1 + t / alph))) <= e^-40.5
+  // for every shape), so the lower-tail value rounds to exactly 1 - in R's pgamma as here - and the masses out there are exactly
+  // zero.  Holds for every valid shape, so the general algorithm skips those days too (they were most of its 301 evaluations for
+  // the sharply peaked delays that need it).
+  if ((alph > 0.0) && (scale > 0.0) && isfinite(alph) && isfinite(scale)) k_hi = (alph + 9.0 * sqrt(alph) + 45.0) * scale;
   put(L.gam + 9, lgam_a1); put(L.gam + 10, logA); put(L.gam + 11, emh); put(L.gam + 12, k_hi);
   // top of the sigma recurrence of the interval-mass coefficients (tile_gamma): ONE short series at m = nct (ratio
   // h / (nct + j) <= 3/8) - serial work, so it belongs to the thread-per-vector pass, not to every lane of a warp
@@ -382,9 +386,12 @@ __device__ inline void tile_gamma(const KModel& m, const RecLayout& L, const Til
     const bool bad = isnan(scale) || isnan(alph) || !(scale > 0.0) || alph < 0.0;
     GammaShape gsh;
     if (!bad) gsh = gamma_shape(alph);
+    const double k_hi = w.rec[L.gam + 12];
+    const int kone = (bad || k_hi >= (double)T) ? T + 1 : min(T + 1, (int)k_hi + 2);  // first day whose value is exactly 1
     for (int k = lane; k <= T; k += 32) {
       double v;
       if (bad) v = (isnan(scale) || isnan(alph)) ? (scale + alph) : d_nan();
+      else if (k >= kone) v = 1.0;
       else v = pgamma_lower_shared(gsh, (double)k / scale);
       P[k] = v;
     }
@@ -643,8 +650,7 @@ __device__ __noinline__ void conv_fixup_tiny(int T, const double* __restrict__ x
 // out there are skipped without changing a bit (short delays: most of the triangle for sod < 0.5).
 __device__ inline int conv_lag_blocks(const KModel& m, const RecLayout& L, const double* rec) {
   const int nb = (m.T + 7) >> 3;
-  if (rec[L.gam + 8] == 0.0) return nb;  // general algorithm: keep everything
-  const double k_hi = rec[L.gam + 12];
+  const double k_hi = rec[L.gam + 12];   // +inf for an invalid shape: keep everything
   if (!(k_hi < (double)m.T)) return nb;
   const int kend = (int)k_hi + 2;                     // first day whose mass is exactly zero (tile_gamma)
   return min(nb, ((kend + 14) >> 3) + 1);            // block dl holds lags 8 dl - 7 .. 8 dl + 7
