@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2
                                                                                           unsigned int* __restrict__ ticket,
                                                                                           const double* __restrict__ theta, long long ld) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned int s_ticket;
+  __shared__ unsigned int s_ticket[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const RecLayout L = rec_layout(m.K, m.A, m.S);
   const TileTables tb = tile_tables_load(m, nullptr);
@@ -219,13 +219,15 @@ __global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2
   tile_smem_init(w);
   // dynamic queue of CTA tiles (kPhase2Tile vectors per warp) in bucket order (heavy regimes first): a CTA that drew cheap
   // vectors comes back for more, so the launch ends within one short tile of the ideal instead of one long tile of the
-  // worst regime
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const long long c0 = (long long)s_ticket * (kPhase2Tile * p2_warps(NT));
+  // worst regime.  The ticket of the NEXT tile is drawn at the start of the current one and published at its end (two slots),
+  // so the round trip of the atomic is hidden behind the evaluations instead of stalling the whole CTA once per tile.
+  if (threadIdx.x == 0) s_ticket[0] = atomicAdd(ticket, 1u);
+  __syncthreads();
+  for (unsigned int it = 0;; it++) {
+    const long long c0 = (long long)s_ticket[it & 1] * (kPhase2Tile * p2_warps(NT));
     if (c0 >= n) break;
+    unsigned int next_ticket = 0;
+    if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
     const long long t0 = c0 + (long long)warp * kPhase2Tile;
     const long long pos = t0 + lane;
     const int vl = (lane < kPhase2Tile && pos < n) ? perm[pos] : 0;
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2
       cta_phase2_impl<NT>(m, L, w, tb, rec + v, cap, e < cnt, [&](int i) { return theta[(long long)i * ld + v]; });
 #else
 #if CC_P2_SYNC == 1
-      __syncthreads();  // the warps of the CTA start every evaluation together
+      if (e) __syncthreads();  // the warps of the CTA start every evaluation together (the first of a tile: behind the ticket barrier)
 #endif
       if (e < cnt) {
         const long long v = __shfl_sync(0xffffffffu, vl, e);
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2
       }
 #endif
     }
+    if (threadIdx.x == 0) s_ticket[(it + 1) & 1] = next_ticket;
+    __syncthreads();
   }
 }
 
