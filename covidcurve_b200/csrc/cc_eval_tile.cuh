@@ -132,17 +132,18 @@ __device__ inline void p1_weights(const KModel& m, const RecLayout& L, Par par, 
 
 // the same, by a whole warp on a record in shared memory: one stratum per lane for the divisions, the two sums in the
 // serial order of the scalar version (identical values)
+// `keep_ne`: rec[L.ne + a] already holds the weights of this parameter vector (the proposal moved none of the noise scalars)
 template <typename Par>
-__device__ inline void p1_weights_warp(const KModel& m, const RecLayout& L, Par par, double* rec) {
+__device__ inline void p1_weights_warp(const KModel& m, const RecLayout& L, Par par, double* rec, bool keep_ne = false) {
   const int A = m.A, lane = threadIdx.x & 31;
   double nedom = 0.0;
-  if (A > 1)
+  if (A > 1 && !keep_ne)
     for (int a = 0; a < A; a++) nedom += par(m.idx_noise[a]) * (double)m.demog[a];
   for (int a = lane; a < A; a += 32) {
     const int r = m.idx_ifr[a];
     double ma = par(r);
     if (m.reparam_ifr && r != m.idx_max_ma) ma = ma * par(m.idx_max_ma);
-    const double ne = (A > 1) ? (par(m.idx_noise[a]) * (double)m.demog[a]) / nedom : (m.binomial ? 1.0 : 0.0);
+    const double ne = keep_ne ? rec[L.ne + a] : (A > 1) ? (par(m.idx_noise[a]) * (double)m.demog[a]) / nedom : (m.binomial ? 1.0 : 0.0);
     rec[L.ne + a] = ne;
     rec[L.nm + a] = ne * ma;
   }

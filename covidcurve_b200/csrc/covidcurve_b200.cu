@@ -359,7 +359,8 @@ __device__ inline SweepSmem carve_sweep(double* q, int d, const SweepCacheLayout
 
 enum : int { kDepWeights = 1, kDepSpline = 2, kDepGamma = 4, kDepSero = 8,
              kKeepL3 = 16,   // the proposal cannot change the serology term (an IFR, the onset-to-death delay)
-             kKeepL2 = 32 }; // the proposal cannot change the age split (test sensitivity / specificity, seroconversion, seroreversion)
+             kKeepL2 = 32,   // the proposal cannot change the age split (test sensitivity / specificity, seroconversion, seroreversion)
+             kKeepNe = 64 }; // the proposal cannot change the attack-rate weights ne[a] (every parameter but the noise scalars)
 
 template <typename T>
 __device__ __forceinline__ void swap_ptr(T*& a, T*& b) { T* t = a; a = b; b = t; }
@@ -507,7 +508,8 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
       auto par = [&](int j) { return j == i ? thp : w.pcur[j]; };
       for (int f = lane; f < L.F; f += 32) w.recB[f] = w.recA[f];
       __syncwarp();
-      if ((dep & kDepWeights) || unbuilt) p1_weights_warp(m, L, par, w.recB);
+      // (a proposal that cannot move the attack-rate weights keeps them: no normalising sum, no divisions)
+      if ((dep & kDepWeights) || unbuilt) p1_weights_warp(m, L, par, w.recB, (dep & kKeepNe) && !unbuilt);
       if (lane == 0) {
         auto putB = [&](int f, double v) { w.recB[f] = v; };
         bool ok = w.recB[L.flags] != 0.0;
@@ -542,7 +544,10 @@ __global__ void __launch_bounds__(32 * kSweepWarps, CC_SWEEP_CTAS) mcmc_sweep_ca
         if (do_gamma) tile_gamma<NT>(m, L, view(w.recB), tb);
         if (do_spline) tot_p = stage_spline<NT>(m, L, w.recB, w.xs);
         else if (need_conv || need_surv) warp_copy(w.xs + kXsLead, cache + CL.xs + kXsLead, CL.nxs - kXsLead);
-        const bool ok = stage_popn(m, L, w.recB, tot_p);
+        // population check (binomial.cpp:170-184): ne[a] * sum(infxn) against the stratum sizes - with the weights and the curve
+        // untouched the outcome is the one the current state recorded
+        const bool same_popn = (dep & kKeepNe) && !do_spline && !cur_noarrays && !unbuilt;
+        const bool ok = same_popn ? (w.recA[L.o_status] == 0.0) : stage_popn(m, L, w.recB, tot_p);
         if (lane == 0) w.recB[L.o_status] = ok ? 0.0 : 1.0;
         __syncwarp();
         if (ok) {
@@ -1005,6 +1010,9 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
     for (int i = 0; i < d; i++) {
       const int roles = ((dep[i] & kDepWeights) ? 1 : 0) + ((dep[i] & kDepSpline) ? 1 : 0) + ((dep[i] & kDepGamma) ? 1 : 0) + ((dep[i] & kDepSero) ? 1 : 0);
       if (roles != 1 || ((dep[i] & kKeepL2) && (dep[i] & kKeepL3))) dep[i] &= ~(kKeepL2 | kKeepL3);
+      bool noise = false;
+      for (int a = 0; a < A && A > 1; a++) noise = noise || (de->idx_noise[a] == i);
+      if (!noise) dep[i] |= kKeepNe;
     }
   }
   std::vector<double> sa(de->sero_a, de->sero_a + (size_t)S * A), sb(de->sero_b, de->sero_b + (size_t)S * A);

@@ -33,7 +33,10 @@ for l in dis[start + 1:]:
             fresh = False
         chain.append((m.group(1), int(m.group(2))))
         mine = [c for c in chain if ours(c[0])]
-        if os.environ.get("NCU_LINES_OUTER"):  # attribute to the line of the top-level evaluation function (stage view)
+        if os.environ.get("NCU_LINES_OUTER") == "2":  # attribute to the statement of the kernel body (covidcurve_b200.cu) it was inlined into
+            body = [c for c in chain if c[0].endswith("covidcurve_b200.cu")]
+            cur = body[-1] if body else chain[-1]
+        elif os.environ.get("NCU_LINES_OUTER"):  # attribute to the line of the top-level evaluation function (stage view)
             body = [c for c in chain if c[0].endswith("cc_eval_tile.cuh")]
             cur = body[-1] if body else chain[-1]
         else:
