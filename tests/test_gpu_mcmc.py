@@ -245,9 +245,10 @@ def test_posterior_agrees_with_the_stored_reference_fit(built_lib, modfit):
     assert 0.20 < acc.mean() < 0.26 and abs(float(np.mean(g["move_rate"])) - 0.23) < 0.02
 
 
-@pytest.mark.parametrize("cfg", ["cfg2", "cfg3"])
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4"])
 def test_posterior_agrees_with_the_oracle_cpu_sampler(built_lib, cfg):
-    """north_star correctness check #2 on BASELINE configs[1] and configs[2]: the GPU engine (other seed, tempered ladder, more
+    """north_star correctness check #2 on BASELINE configs[1], configs[2] and configs[3] (cfg4: 17 age bands x 400 days, d = 48;
+    oracle fixture of 8 chains x 15 000 iterations): the GPU engine (other seed, tempered ladder, more
     chains) and the CPU oracle's drjacoby-equivalent sampler driving the restated reference likelihood
     (tests/golden/oracle_mcmc_*.npz, made by tests/golden/make_mcmc_golden.py: 8 chains x 20 000 single-rung iterations) sample
     the same posterior: every parameter of the GPU run has R-hat < 1.1; for every parameter the oracle run itself has mixed
