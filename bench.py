@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--no-mcmc", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline likelihood leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-shapes", action="store_true", help="skip the cfg2 / cfg4 likelihood figures")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -353,6 +354,34 @@ def main():
             model.loglike_ptr(d_near.data_ptr(), V, V, d_out2.data_ptr(), _lib.CC_MEM_DEVICE, stream)
         value_post = V * args.steps / (timed_device(d_near, d_out2, V, args.steps) * 1e-3)
         del d_near, near, d_out2
+
+    # ---------------------------------------------------------------- the other BASELINE shapes, device-resident (N = 1 only): cfg2
+    # (5 x 200, logit-normal serology, seroreversion: the hazard convolution is a second Toeplitz product) and cfg4 (17 x 400)
+    other_shapes = None
+    if world == 1 and not args.no_other_shapes:
+        other_shapes = {}
+        for cfg_o in ("cfg2", "cfg4"):
+            spec_o, truth_o = synth.make_spec(cfg_o)
+            model_o = _lib.Model(spec_o, device=local_rank)
+            Vo = 1 << 18
+            th_o = synth.random_theta(spec_o, Vo, seed=synth.SEED_THETA + 7, bad_frac=0.01)
+            d_tho = torch.from_numpy(np.ascontiguousarray(th_o.T)).to(dev)
+            d_outo = torch.empty(Vo, dtype=torch.float64, device=dev)
+            for _ in range(2):
+                model_o.loglike_ptr(d_tho.data_ptr(), Vo, Vo, d_outo.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                model_o.loglike_ptr(d_tho.data_ptr(), Vo, Vo, d_outo.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            rate_o = Vo * args.steps / (e0.elapsed_time(e1) * 1e-3)
+            full_o = float(np.mean(d_outo.cpu().numpy() != _lib.CC_OVERFLO_LOGLIKE))
+            other_shapes[cfg_o] = {"value": rate_o, "unit": UNIT, "vectors_per_step": Vo, "d": spec_o.d, "flops_per_eval": f_alg(spec_o),
+                                   "full_eval_fraction": full_o, "_falg_rate": rate_o * f_alg(spec_o) * full_o / 1e12}
+            del d_tho, d_outo, th_o
+            model_o.close()
 
     # ---------------------------------------------------------------- end-to-end leg (host buffers through the C ABI)
     def timed_host(theta_ptr, out_ptr, steps):
@@ -605,6 +634,8 @@ def main():
             "gpu_launches": args.steps * launches_per_step,
             "posterior_like": None if value_post is None else {"value": value_post, "unit": UNIT, "frac_of_fp64_peak": value_post * falg / 1e12 / peak_tf,
                                                                 "vectors": "truth x (1 + 0.02 N(0,1)), clipped to the box"},
+            "other_shapes": None if other_shapes is None else {k: dict({kk: vv for kk, vv in v.items() if kk != "_falg_rate"},
+                                                                       frac_of_fp64_peak=v["_falg_rate"] / peak_tf) for k, v in other_shapes.items()},
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "mcmc": mcmc, "mcmc_cfg3": mcmc3, "collective": collective,
         }
         print(json.dumps(out))

@@ -13,7 +13,7 @@ if [ "${2:-}" != "skip-tests" ] && [ "${2:-}" != "caps-only" ]; then
 fi
 if [ "${2:-}" != "caps-only" ]; then
 python bench.py > $O/${TAG}_bench_default.json 2> $O/${TAG}_bench_default.err; echo "default bench rc=$?"
-CMD="python bench.py --steps 2 --warmup 3 --vectors 262144 --mcmc-iters 4 --mcmc-settle 6 --mcmc-chains 512 --cfg3-seconds 0.05 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --vectors 262144 --mcmc-iters 4 --mcmc-settle 6 --mcmc-chains 512 --cfg3-seconds 0.05 --no-cpu-baseline --no-other-shapes"
 $CMD > $O/${TAG}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_l.log 2>&1
 fi
 cap() {  # name, kernel regex, skip, mangled substring, command
