@@ -356,12 +356,13 @@ def main():
         del d_near, near, d_out2
 
     # ---------------------------------------------------------------- the other BASELINE shapes, device-resident (N = 1 only): cfg2
-    # (5 x 200, logit-normal serology, seroreversion: the hazard convolution is a second Toeplitz product) and cfg4 (17 x 400)
+    # (5 x 200, logit-normal serology, seroreversion: the hazard convolution is a second Toeplitz product), cfg4 (17 x 400), and
+    # cfg3 / cfg4 with seroreversion ("also report yes")
     other_shapes = None
     if world == 1 and not args.no_other_shapes:
         other_shapes = {}
-        for cfg_o in ("cfg2", "cfg4"):
-            spec_o, truth_o = synth.make_spec(cfg_o)
+        for cfg_o, rev_o in (("cfg2", None), ("cfg4", None), ("cfg3", True), ("cfg4", True)):
+            spec_o, truth_o = synth.make_spec(cfg_o, serorev=rev_o)
             model_o = _lib.Model(spec_o, device=local_rank)
             Vo = 1 << 18
             th_o = synth.random_theta(spec_o, Vo, seed=synth.SEED_THETA + 7, bad_frac=0.01)
@@ -378,7 +379,7 @@ def main():
             torch.cuda.synchronize()
             rate_o = Vo * args.steps / (e0.elapsed_time(e1) * 1e-3)
             full_o = float(np.mean(d_outo.cpu().numpy() != _lib.CC_OVERFLO_LOGLIKE))
-            other_shapes[cfg_o] = {"value": rate_o, "unit": UNIT, "vectors_per_step": Vo, "d": spec_o.d, "flops_per_eval": f_alg(spec_o),
+            other_shapes[cfg_o + ("_serorev" if rev_o else "")] = {"value": rate_o, "unit": UNIT, "vectors_per_step": Vo, "d": spec_o.d, "flops_per_eval": f_alg(spec_o),
                                    "full_eval_fraction": full_o, "_falg_rate": rate_o * f_alg(spec_o) * full_o / 1e12}
             del d_tho, d_outo, th_o
             model_o.close()
@@ -428,7 +429,7 @@ def main():
         return {"states": int(len(th)), "max_rel_err_vs_oracle": float(rel.max()) if rel.size else 0.0,
                 "failure_value_mismatches": int(np.sum(bad & (chk != got)))}
 
-    mcmc = mcmc3 = collective = None
+    mcmc = mcmc2 = mcmc3 = collective = None
     if not args.no_mcmc:
         # ---- cfg3: 64 chains x 50 rungs on ONE GPU (BASELINE configs[2]); every rank runs its own 64 chains when N > 1
         chains3, rungs3 = truth["chains"], truth["rungs"]
@@ -456,6 +457,26 @@ def main():
         if rank == 0:
             mcmc3["check"] = oracle_check(spec, mc.fetch(), 64)
         mc.close()
+
+        # ---- cfg2: 4 chains x 20 rungs (BASELINE configs[1]; 80 particles: a tenth of one wave of warps - reported for completeness)
+        mcmc2 = None
+        if world == 1:
+            spec2, truth2 = synth.make_spec("cfg2")
+            model2 = _lib.Model(spec2, device=local_rank)
+            init2 = np.tile(synth.true_theta(spec2, truth2), (truth2["chains"], 1))
+            it2 = 1500
+            mc2 = _lib.Mcmc(model2, burnin=100 + it2 + 2, samples=0, rungs=truth2["rungs"], chains=truth2["chains"], seed=synth.SEED_MCMC,
+                            record_rungs=False, init=init2, thin=50)
+            mc2.advance(100)
+            mc2.advance(it2)
+            P2 = truth2["chains"] * truth2["rungs"]
+            mcmc2 = {"iter_per_sec_all_chains_x_rungs": P2 * it2 / (mc2.last_advance_ms * 1e-3), "chains": truth2["chains"], "rungs": truth2["rungs"],
+                     "iterations_timed": it2, "ms_per_iteration": mc2.last_advance_ms / it2,
+                     "loglike_evals_per_sec": P2 * it2 * spec2.d / (mc2.last_advance_ms * 1e-3),
+                     "workload": "cfg2: 5 age bands x 200 days, logit-normal serology, seroreversion, d=%d, 4 chains x 20 rungs" % spec2.d,
+                     "check": oracle_check(spec2, mc2.fetch(), 4)}
+            mc2.close()
+            model2.close()
 
         # ---- cfg4: 4096 chains x 64 rungs sharded over the ranks (BASELINE configs[3])
         spec4, truth4 = synth.make_spec("cfg4")
@@ -584,6 +605,8 @@ def main():
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             "traffic": traffic["bytes_per_eval"] * Vs if traffic else None, "traffic_source": traffic_src,
+            # hardware view of the same kernel from the same capture: the FP64 vector and tensor sub-pipes share one pipe
+            "ncu": (traffic or {}).get("ncu"),
             "algorithmic_bytes": float(alg_bytes),
             "kernel": "loglike_phase2_kernel (the per-day pass; kernel_ms covers the whole pipeline of one cc_loglike_batch call)",
             "kernel_ms": kern_ms, "vectors_per_launch": Vs, "flops_per_eval": falg, "full_eval_fraction": full_frac,
@@ -615,7 +638,7 @@ def main():
                                       "mod": float(theta[i, spec.index("mod")])} for i in worst]}
             if not args.no_mcmc:
                 cpu["mcmc"] = {"cfg3_all_cores": cpu_mcmc_rate("cfg3", cores, 6.0), "cfg3_1_core": cpu_mcmc_rate("cfg3", 1, 5.0),
-                               "cfg4_all_cores": cpu_mcmc_rate("cfg4", cores, 8.0),
+                               "cfg4_all_cores": cpu_mcmc_rate("cfg4", cores, 8.0), "cfg2_all_cores": cpu_mcmc_rate("cfg2", cores, 4.0),
                                "note": "oracle port of drjacoby's loop (one chain per thread, 4 rungs): chain-rung iterations/s, the unit of `mcmc`"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -636,7 +659,7 @@ def main():
                                                                 "vectors": "truth x (1 + 0.02 N(0,1)), clipped to the box"},
             "other_shapes": None if other_shapes is None else {k: dict({kk: vv for kk, vv in v.items() if kk != "_falg_rate"},
                                                                        frac_of_fp64_peak=v["_falg_rate"] / peak_tf) for k, v in other_shapes.items()},
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "mcmc": mcmc, "mcmc_cfg3": mcmc3, "collective": collective,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "mcmc": mcmc, "mcmc_cfg3": mcmc3, "mcmc_cfg2": mcmc2, "collective": collective,
         }
         print(json.dumps(out))
     if world > 1:
