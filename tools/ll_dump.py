@@ -11,7 +11,7 @@ if "--cmp" in sys.argv:
           np.array_equal(a == bad, b == bad), np.max(np.abs(a[ok] - b[ok]) / np.abs(a[ok])) if ok.any() else 0.0))
     sys.exit(0)
 from covidcurve_b200 import _lib, synth
-spec, truth = synth.make_spec("cfg3")
+spec, truth = synth.make_spec(os.environ.get("LL_CFG", "cfg3"), serorev=True if os.environ.get("LL_SEROREV") else None)
 model = _lib.Model(spec, device=0)
 n = 1 << 17
 box = synth.random_theta(spec, n, seed=synth.SEED_THETA, bad_frac=0.01)
