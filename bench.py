@@ -294,16 +294,36 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    def timed_device(d_theta, d_out, n, steps):
-        """K back-to-back device-resident passes; returns ms (max over ranks)."""
+    L2_BYTES = 126e6
+    flush_buf = [None]
+
+    def timed_device(d_theta, d_out, n, steps, mdl=None, dd=None):
+        """K device-resident passes; returns ms (max over ranks).  Inputs larger than L2: the K passes run back to back between one pair
+        of events.  Inputs that would fit in L2 (the strong split at N >= 4): a 256 MB buffer is written between the passes, outside
+        the timed regions - every pass is bracketed by its own pair of events on the launching stream and the K durations are summed."""
+        mdl, dd = mdl or model, dd or d
+        if dd * n * 8 > L2_BYTES:
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                mdl.loglike_ptr(d_theta.data_ptr(), n, n, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+            e1.record()
+            barrier()
+            return reduce_ranks(e0.elapsed_time(e1))
+        if flush_buf[0] is None:
+            flush_buf[0] = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        evs = []
         for _ in range(steps):
-            model.loglike_ptr(d_theta.data_ptr(), n, n, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
-        e1.record()
+            flush_buf[0].fill_(1)                      # evicts theta and the work buffers of the previous pass from the 126 MB L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mdl.loglike_ptr(d_theta.data_ptr(), n, n, d_out.data_ptr(), _lib.CC_MEM_DEVICE, stream)
+            e1.record()
+            evs.append((e0, e1))
         barrier()
-        return reduce_ranks(e0.elapsed_time(e1))
+        return reduce_ranks(sum(a.elapsed_time(b) for a, b in evs))
 
     # ---------------------------------------------------------------- strong split of the V vectors (value)
     theta_all = synth.random_theta(spec, V, seed=synth.SEED_THETA, bad_frac=0.01)      # the same V vectors on every rank
@@ -370,14 +390,7 @@ def main():
             d_outo = torch.empty(Vo, dtype=torch.float64, device=dev)
             for _ in range(2):
                 model_o.loglike_ptr(d_tho.data_ptr(), Vo, Vo, d_outo.data_ptr(), _lib.CC_MEM_DEVICE, stream)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                model_o.loglike_ptr(d_tho.data_ptr(), Vo, Vo, d_outo.data_ptr(), _lib.CC_MEM_DEVICE, stream)
-            e1.record()
-            torch.cuda.synchronize()
-            rate_o = Vo * args.steps / (e0.elapsed_time(e1) * 1e-3)
+            rate_o = Vo * args.steps / (timed_device(d_tho, d_outo, Vo, args.steps, model_o, spec_o.d) * 1e-3)
             full_o = float(np.mean(d_outo.cpu().numpy() != _lib.CC_OVERFLO_LOGLIKE))
             other_shapes[cfg_o + ("_serorev" if rev_o else "")] = {"value": rate_o, "unit": UNIT, "vectors_per_step": Vo, "d": spec_o.d, "flops_per_eval": f_alg(spec_o),
                                    "full_eval_fraction": full_o, "_falg_rate": rate_o * f_alg(spec_o) * full_o / 1e12}
@@ -645,9 +658,9 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "vectors_per_step": V, "vectors_per_gpu_per_step": Vs, "layout": "SoA theta[d][V]",
-                       "l2": "inputs larger than L2 (%.0f MB per GPU per step)" % (d * Vs * 8 / 1e6) if d * Vs * 8 > 126e6 else
-                             "inputs of %.0f MB per GPU per step: the likelihood reads each value once, L2 residency of theta is irrelevant "
-                             "(FP64-bound, < 1 %% of HBM bandwidth)" % (d * Vs * 8 / 1e6),
+                       "l2": "inputs larger than L2 (%.0f MB per GPU per step), passes back to back" % (d * Vs * 8 / 1e6) if d * Vs * 8 > 126e6 else
+                             "inputs of %.0f MB per GPU per step would fit in L2: L2 flushed between the timed passes (256 MB written, outside "
+                             "the per-pass event pairs whose durations are summed)" % (d * Vs * 8 / 1e6),
                        "full_eval_fraction": full_frac, "split": "V vectors split evenly over the ranks (SURVEY.md 8e), no collective"},
             "weak": weak,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": d * V * 8, "d2h_bytes_per_step": V * 8, "steps": e2e_steps,
