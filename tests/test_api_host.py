@@ -114,6 +114,33 @@ def test_geweke_windows_are_codas(monkeypatch):
     assert seen == [(1.0, 5.0, 5), (20.0, 40.0, 21)]
 
 
+def test_spectrum0_ar_against_a_direct_yule_walker_solve():
+    """coda::spectrum0.ar = R's ar.yw (order <= 10 log10 n by AIC, var.pred scaled by n / (n - (p + 1))) evaluated at frequency zero.
+    The Levinson-Durbin recursion of summaries._spectrum0_ar (and of the device kernel that restates it) against an independent
+    route: the Yule-Walker equations of every order solved as Toeplitz systems, the same AIC and the same variance scaling."""
+    from scipy.linalg import solve_toeplitz
+    rng = np.random.default_rng(4)
+    for rho, n in ((0.0, 700), (0.6, 1500), (0.95, 4000), (-0.5, 333)):
+        x = np.zeros(n); e = rng.normal(size=n)
+        for t in range(1, n):
+            x[t] = rho * x[t - 1] + e[t] + (0.3 * e[t - 1] if rho == 0.6 else 0.0)
+        xc = x - x.mean()
+        omax = int(min(n - 1, np.floor(10 * np.log10(n))))
+        r = np.array([np.dot(xc[: n - k], xc[k:]) / n for k in range(omax + 1)])
+        best = (n * np.log(r[0]), r[0], np.zeros(0))
+        for p in range(1, omax + 1):
+            phi = solve_toeplitz(r[:p], r[1:p + 1])
+            v = r[0] - np.dot(phi, r[1:p + 1])
+            aic = n * np.log(v) + 2 * p
+            if aic < best[0]:
+                best = (aic, v, phi)
+        _, v, phi = best
+        want = v * n / (n - (len(phi) + 1)) / (1 - phi.sum()) ** 2
+        got = summaries._spectrum0_ar(x)
+        assert abs(got - want) <= 1e-8 * want, (rho, n, got, want)
+        assert abs(summaries.effective_size(x) - n * x.var(ddof=1) / want) <= 1e-8 * n
+
+
 def test_rhat_from_moments_equals_rhat_from_draws():
     x = np.random.default_rng(1).normal(size=(5, 300, 3)) + np.arange(5)[:, None, None] * 0.1
     np.testing.assert_allclose(summaries.rhat_from_moments(*summaries.chain_moments(x)), summaries.rhat_per_parameter(x))
