@@ -8,7 +8,7 @@ from covidcurve_b200 import _lib, synth
 kind = sys.argv[1] if len(sys.argv) > 1 else "box"
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-spec, truth = synth.make_spec("cfg3")
+spec, truth = synth.make_spec(os.environ.get("LL_CFG", "cfg3"), serorev=True if os.environ.get("LL_SEROREV") else None)
 model = _lib.Model(spec, device=0)
 if kind == "box":
     th = synth.random_theta(spec, V, seed=synth.SEED_THETA, bad_frac=0.01)
