@@ -78,6 +78,7 @@ struct cc_model {
   std::vector<double> pinit;
   int sm_count = 0;
   int grid_p2 = 1;                 // resident CTAs of pass C of the batched likelihood
+  int p2_warps = 4;                // warps per CTA of pass C (chosen at creation, covidcurve_b200.cu: p2_candidates)
   int grid_max = 1;                // resident CTAs of the evaluation kernel on this device
   // work buffers of the batched likelihood, one set per launch slot ([0] device-pointer calls, [1]..[3] the three host-path
   // streams): records rec[F][cap], regime keys, permutation, histogram + cursors; grown on demand

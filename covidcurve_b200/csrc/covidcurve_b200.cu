@@ -72,16 +72,36 @@ constexpr int kWarpsPerCta = 4;
 // collide on the pipe.  Measured on B200, box workload, M evals/s (value / e2e): 5 CTAs x 4 warps free-running 73.8 / 63.5;
 // the same with the barrier 77.9 / 68; 2 x 8: 79.5 / 74.3; 2 x 10: 83.1 / 74.7; 1 x 20: 80.6 / 77.1; 2 x 10 with a barrier
 // per stage 78.9 / 74.9 (profiles/r1_summary.md).
+// The shape is chosen per model at creation (cc_model_create) among a few candidates, the one with the most resident warps per SM
+// that fits the model's shared memory: p2_warps(nt) is the LARGEST CTA a kernel instantiation is compiled for (launch bounds), the
+// kernel itself reads its warp count from blockDim.
+struct P2Shape { int warps, ctas; };
 #ifdef CC_P2_WARPS
 __host__ __device__ constexpr int p2_warps(int) { return CC_P2_WARPS; }
 #else
-__host__ __device__ constexpr int p2_warps(int nt) { return nt <= 5 ? 10 : nt <= 7 ? 7 : 6; }  // 11.2 / 15.3 / 33 kB of shared memory per warp
+__host__ __device__ constexpr int p2_warps(int nt) { return nt <= 4 ? 12 : nt <= 5 ? 10 : nt <= 7 ? 15 : 6; }
 #endif
 #ifdef CC_P2_CTAS
 __host__ __device__ constexpr int p2_ctas(int) { return CC_P2_CTAS; }
 #else
-__host__ __device__ constexpr int p2_ctas(int nt) { return nt <= 7 ? 2 : 1; }
+__host__ __device__ constexpr int p2_ctas(int nt) { return nt <= 5 ? 2 : 1; }
 #endif
+// candidates in order of preference (measured on B200, M evals/s box / posterior-like: T = 200 2 x 12 warps 92.9 / 93.8 against 2 x 10
+// 90.5 / 92.9; T = 300 2 x 10 (2 x 11, 2 x 8, 1 x 20 slower); T = 400 1 x 15 62.4 / 59.0 against 2 x 7 60.1 / 58.0 and 3 x 5 59.6 / 59.1)
+static inline int p2_candidates(int nt, P2Shape* out) {
+#if defined(CC_P2_WARPS) || defined(CC_P2_CTAS)
+  out[0] = {p2_warps(nt), p2_ctas(nt)};
+  return 1;
+#else
+  int n = 0;
+  if (nt <= 4) { out[n++] = {12, 2}; out[n++] = {10, 2}; }
+  else if (nt <= 5) { out[n++] = {10, 2}; }
+  else if (nt <= 7) { out[n++] = {15, 1}; out[n++] = {7, 2}; }
+  else { out[n++] = {6, 1}; }
+  for (int w = p2_warps(nt) - 1; w >= 1 && n < 24; w--) out[n++] = {w, 1};  // models with many strata / knots: whatever still fits
+  return n;
+#endif
+}
 #ifndef CC_MIN_CTAS
 #define CC_MIN_CTAS 4  // resident CTAs per SM the evaluation kernels are compiled for (caps registers at 128 per thread)
 #endif
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(32 * p2_warps(NT), p2_ctas(NT)) loglike_phase2
   if (threadIdx.x == 0) s_ticket[0] = atomicAdd(ticket, 1u);
   __syncthreads();
   for (unsigned int it = 0;; it++) {
-    const long long c0 = (long long)s_ticket[it & 1] * (kPhase2Tile * p2_warps(NT));
+    const long long c0 = (long long)s_ticket[it & 1] * (kPhase2Tile * (int)(blockDim.x >> 5));
     if (c0 >= n) break;
     unsigned int next_ticket = 0;
     if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
@@ -816,7 +836,13 @@ static cudaError_t warp_kernels_opt_in(const KModel& k, int nt) {
   cudaError_t e = cudaSuccess;
 #define CC_OPT(NT_)                                                                                                   \
   if (nt == NT_) {                                                                                                    \
-    e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes / kWarpsPerCta * p2_warps(NT_)); \
+    {                                                                                                                 \
+      cudaFuncAttributes fp;                                                                                          \
+      e = cudaFuncGetAttributes(&fp, loglike_phase2_kernel<NT_>);                                                     \
+      if (e == cudaSuccess)                                                                                           \
+        e = cudaFuncSetAttribute(loglike_phase2_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                 227 * 1024 - (int)fp.sharedSizeBytes);                                               \
+    }                                                                                                                 \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mcmc_init_tile_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
     if (e == cudaSuccess) {                                                                                           \
       cudaFuncAttributes fa;                                                                                          \
@@ -1053,25 +1079,36 @@ extern "C" int cc_model_create(const cc_model_desc* de, int device, cc_model** o
   }
   if (e == cudaSuccess) e = warp_kernels_opt_in(k, m->nt);
   if (e == cudaSuccess) {
-    int bps = 0;
-    const size_t sm_bytes = warp_cta_smem(k, m->nt);
-    const int p2w = p2_warps(m->nt);
-    const size_t p2_bytes = sm_bytes / kWarpsPerCta * p2w;
-    switch (m->nt) {
-#define CC_OCC(NT_) case NT_: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_phase2_kernel<NT_>, 32 * p2_warps(NT_), p2_bytes); break;
-      CC_FOR_EACH_NT(CC_OCC)
+    // shape of the per-day pass: the candidate with the most resident warps per SM that fits this model's shared memory
+    const size_t per_warp = warp_cta_smem(k, m->nt) / kWarpsPerCta;
+    P2Shape cand[24];
+    const int nc = p2_candidates(m->nt, cand);
+    int best_w = 0, best_bps = 0;
+    for (int c = 0; c < nc && e == cudaSuccess; c++) {
+      const size_t bytes = per_warp * cand[c].warps;
+      if (bytes > 227 * 1024 - 1040) continue;
+      int bps = 0;
+      cudaError_t oe = cudaSuccess;
+      switch (m->nt) {
+#define CC_OCC(NT_) case NT_: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, loglike_phase2_kernel<NT_>, 32 * cand[c].warps, bytes); break;
+        CC_FOR_EACH_NT(CC_OCC)
 #undef CC_OCC
-      default: break;
+        default: break;
+      }
+      if (oe != cudaSuccess) { cudaGetLastError(); continue; }
+      bps = std::min(bps, cand[c].ctas);
+      if (bps * cand[c].warps > best_bps * best_w) { best_w = cand[c].warps; best_bps = bps; }
     }
-    if (e == cudaSuccess && bps < 1) {
+    if (e == cudaSuccess && best_w < 1) {
       cc_model_destroy(m);
       return fail(CC_E_INVALID, "model too large for one CTA's shared memory");
     }
-    m->grid_p2 = std::max(1, bps) * m->sm_count;
-    m->grid_max = std::max(1, bps * p2w / kWarpsPerCta) * m->sm_count;  // in 4-warp CTAs (initial-state kernel of the sweep)
+    m->p2_warps = best_w;
+    m->grid_p2 = std::max(1, best_bps) * m->sm_count;
+    m->grid_max = std::max(1, best_bps * best_w / kWarpsPerCta) * m->sm_count;  // in 4-warp CTAs (initial-state kernel of the sweep)
     if (std::getenv("CC_VERBOSE"))
-      std::fprintf(stderr, "covidcurve_b200: per-day pass %d CTAs/SM x %d warps, %zu B smem/CTA, persistent grid %d\n", bps, p2w,
-                   p2_bytes, m->grid_p2);
+      std::fprintf(stderr, "covidcurve_b200: per-day pass %d CTAs/SM x %d warps, %zu B smem/CTA, persistent grid %d\n", best_bps, best_w,
+                   per_warp * best_w, m->grid_p2);
   }
   const size_t smem = eval_smem_bytes(d, T, T);
   if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(curves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1153,7 +1190,7 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
   const unsigned gridA = (unsigned)((n + 127) / 128);
   const size_t smem = warp_cta_smem(k, m->nt);
   const long long tiles = (n + kPhase2Tile - 1) / kPhase2Tile;
-  const int p2w = p2_warps(m->nt);
+  const int p2w = m->p2_warps;
   const unsigned gridC = (unsigned)std::min<long long>((tiles + p2w - 1) / p2w, (long long)m->grid_p2);
   switch (m->nt) {
 #define CC_LAUNCH(NT_)                                                                                                        \
@@ -1161,7 +1198,7 @@ static int launch_loglike(cc_model* m, const double* d_theta, long long n, long 
     loglike_phase1_kernel<NT_><<<gridA, 128, 0, st>>>(k, d_theta, n, ld, wk.rec, wk.cap, wk.key, counts);                     \
     bucket_offsets_kernel<<<1, 1, 0, st>>>(counts, cursor);                                                                   \
     bucket_scatter_kernel<<<gridA, 128, 0, st>>>(wk.key, n, cursor, wk.perm);                                                 \
-    loglike_phase2_kernel<NT_><<<gridC, 32 * p2_warps(NT_), smem / kWarpsPerCta * p2_warps(NT_), st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 2 * kNumKeys, d_theta, ld);                      \
+    loglike_phase2_kernel<NT_><<<gridC, 32 * p2w, smem / kWarpsPerCta * p2w, st>>>(k, n, wk.rec, wk.cap, wk.perm, counts + 2 * kNumKeys, d_theta, ld);                      \
     loglike_phase3_kernel<<<gridA, 128, 0, st>>>(k, n, wk.rec, wk.cap, d_out);                                                \
     break;
     CC_FOR_EACH_NT(CC_LAUNCH)
